@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Headline benchmark: settles/sec on the serving batch (BASELINE.json configs[2]:
+B independent lattices N=1200 D=384 k=8 settled concurrently on one B200).
+
+One STEP = the reference's per-request sequence for every lattice of the batch
+(cloud/app/main.py:916-939,1043,1061; scripts/benchmark.py:50-70):
+    build (ctor) + set_query + settle(max_iters=12, tol=1e-3) + light receipt (U* solve + deltaH)
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+`value`  : lattices/s with the anchors already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the public API with HOST buffers: pinned Y/psi -> H2D, build, settle,
+           receipt, D2H of the per-lattice results, all inside the timed region.
+`roofline`: the dominant kernel of the step, timed live with CUDA events on the launching stream.
+`cpu_baseline` / --impl reference: the oracle's dense literal restatement of the reference
+           (oracle/dense.py, kind "port": the reference is Python and cannot travel to the GPU box)
+           on the host cores.
+Multi-GPU: lattices are independent -> replicas only (the batch is sharded, no collective on the
+data path); scaling is weak (B lattices per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_LAT, D_LAT, K_LAT = 1200, 384, 8
+METRIC = "settles/sec (N=1200,D=384 batched)"
+UNIT = "lattices/s"
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_reference_rate(n_lattices: int, workers: int) -> dict:
+    """Time the dense oracle (reference restatement) on `n_lattices` lattices using `workers`
+    processes (BLAS single-threaded inside each, which is the throughput-optimal CPU layout)."""
+    import multiprocessing as mp
+
+    from oracle import cpu_bench
+
+    ctx = mp.get_context("spawn")
+    old = {k: os.environ.get(k) for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in old:
+        os.environ[k] = "1"
+    try:
+        with ctx.Pool(workers) as pool:
+            pool.map(cpu_bench.settle_one, range(workers))  # warm-up: imports + first BLAS call
+            t0 = time.perf_counter()
+            out = pool.map(cpu_bench.settle_one, range(n_lattices), chunksize=1)
+            dt = time.perf_counter() - t0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return {"value": n_lattices / dt, "seconds": dt, "deltaH0": out[0]}
+
+
+def host_workers() -> int:
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = host_workers()
+    per_step = max(workers, 16)
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_reference_rate(workers, workers)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        r = cpu_reference_rate(per_step, workers)
+        t_total += r["seconds"]
+        n_total += per_step
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"serving batch: independent lattices N={N_LAT} D={D_LAT} k={K_LAT}, "
+                               "build + settle(12,1e-3) + light receipt per lattice",
+                   "lattices_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{per_step} lattices/step x {args.steps} steps, dense oracle "
+                                   f"(oracle/dense.py) in {workers} processes, 1 BLAS thread each"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oscillink_b200 import BatchedLattices
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    # synthetic Gaussian anchors; psi_b = normalise(mean(Y_b[:32]))  (scripts/benchmark.py:45-48)
+    Y = torch.randn((B, N_LAT, D_LAT), generator=gen, device=dev, dtype=torch.float32)
+    psi = Y[:, :32, :].mean(dim=1)
+    psi = psi / (psi.norm(dim=1, keepdim=True) + 1e-12)
+    Y_host = torch.empty((B, N_LAT, D_LAT), dtype=torch.float32, pin_memory=True)
+    Y_host.copy_(Y)
+    psi_host = torch.empty((B, D_LAT), dtype=torch.float32, pin_memory=True)
+    psi_host.copy_(psi)
+    res_host = torch.empty((B, 5), dtype=torch.float64, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        bl = BatchedLattices(Y, kneighbors=K_LAT)
+        bl.set_query(psi)
+        out = bl.settle(max_iters=12, tol=1e-3, receipt=True)
+        return bl, out
+
+    def step_e2e():
+        Yd = Y_host.to(dev, non_blocking=True)
+        pd = psi_host.to(dev, non_blocking=True)
+        bl = BatchedLattices(Yd, kneighbors=K_LAT)
+        bl.set_query(pd)
+        out = bl.settle(max_iters=12, tol=1e-3, receipt=True)
+        pack = torch.stack([out["iters"].double(), out["res"].double(), out["ustar_iters"].double(),
+                            out["ustar_res"].double(), out["deltaH"]], dim=1)
+        res_host.copy_(pack, non_blocking=True)
+        return bl, out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        phases = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            bl, _ = fn()
+            phases.append(bl.events)
+            del bl
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, phases
+
+    for _ in range(max(args.warmup, 3)):
+        bl, out = step_resident()
+        del bl
+    torch.cuda.synchronize()
+    check = {"iters_mean": float(out["iters"].mean().item()),
+             "ustar_iters_mean": float(out["ustar_iters"].mean().item()),
+             "deltaH_mean": float(out["deltaH"].mean().item())}
+    engine = None
+    with ClockSampler(local) as clk:
+        ms, phases = timed(step_resident, args.steps)
+    clocks = clk.summary()
+    # per-kernel device time, averaged over the timed steps
+    torch.cuda.synchronize()
+    kern = {}
+    for ev in phases:
+        for name, (a, b) in ev.items():
+            kern.setdefault(name, []).append(a.elapsed_time(b))
+    kern_ms = {k: sum(v) / len(v) for k, v in kern.items()}
+    bl, _ = step_resident()
+    engine = getattr(bl, "engine_used", "simt")
+    nnz_mean = float(bl.nnz.double().mean().item())
+    del bl
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms / 1000.0)
+    e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_src = "measured"
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+        peak_src = "fallback"
+    dom = max(kern_ms, key=kern_ms.get)
+    if dom == "knn_candidates":
+        flops = 2.0 * N_LAT * N_LAT * D_LAT * B  # 2 N^2 D per lattice
+        achieved = flops / (kern_ms[dom] / 1000.0) / 1e12
+        # TF32 tensor rate is half the bf16 rate; denominator derived from the measured bf16 peak
+        peak = 0.5 * float(peaks["bf16_tflops_sustained"])
+        roof = {"kernel": "knn_candidates(" + engine + ")", "bound": "tensor", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peak_src}: 0.5 x bf16_tflops_sustained (TF32 = half bf16 rate)",
+                "algorithmic": "2*N^2*D flops per lattice (3xTF32 issues 3x that on the tensor pipe)"}
+    else:
+        V = N_LAT * D_LAT * 4.0
+        if dom == "batched_settle":
+            byts = (3.0 * V + 12.0 * nnz_mean + 2.0 * V) * B  # SURVEY 8(d) + U* solve re-reads Y, writes nothing else
+        elif dom == "knn_rescore":
+            byts = (K_LAT + 4 + 1) * V * B
+        elif dom == "normalize":
+            byts = 2.0 * V * B
+        else:
+            byts = 3.0 * N_LAT * K_LAT * 8.0 * B
+        achieved = byts / (kern_ms[dom] / 1000.0) / 1e9
+        peak = float(peaks["hbm_gbs"])
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src}
+    roof["kernel_ms_per_step"] = kern_ms
+    roof["share_of_step"] = {k: v / (ms / args.steps) for k, v in kern_ms.items()}
+
+    line = None
+    if rank == 0:
+        workers = host_workers()
+        sample = max(2 * workers, 32)
+        cpu = cpu_reference_rate(sample, workers)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"serving batch: {B} independent lattices N={N_LAT} D={D_LAT} "
+                                   f"k={K_LAT} per GPU; step = build + settle(12,1e-3) + light receipt",
+                       "lattices_per_step_per_gpu": B, "parallelism": f"replicas x{world}",
+                       "l2": "inputs (7.5 GB/step at B=4096) larger than L2", "knn_engine": engine},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(Y_host.numel() * 4 + psi_host.numel() * 4),
+                    "d2h_bytes_per_step": int(res_host.numel() * 8)},
+            "gpu_launches": 8 * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{sample} lattices, dense oracle (oracle/dense.py), "
+                                       f"{workers} processes x 1 BLAS thread"},
+            "check": check,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="lattices per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,247 @@
+/*
+ * oscillink_b200.h -- C ABI of the B200-native lattice-settle hot path.
+ *
+ * The reference (Maverick0351a/Oscillink) has NO FFI: its boundary is the Python class
+ * `OscillinkLattice` (oscillink/core/lattice.py:23) calling NumPy.  Each entry point
+ * below replaces the NumPy expression(s) cited next to it; the Python host mirror
+ * (oscillink_b200/lattice.py) keeps the class surface unchanged and binds these
+ * symbols with ctypes (see INTEGRATION.md for the stub a reference maintainer adds).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Every call returns an int status (OSC_OK == 0); osc_last_error() gives the text of
+ *     the last failure on the calling thread.  No exceptions cross the boundary.
+ *   - Pointers are DEVICE pointers unless the name starts with h_ (host).
+ *   - The caller owns every buffer, including the workspace (query the size first).
+ *   - Every launch goes to the cudaStream_t passed in (as void*); calls are re-entrant
+ *     across host threads (no global mutable state).
+ *   - All arrays are row-major fp32 / int32.  `batch` independent lattices are stored
+ *     back to back ([batch][N][D], [batch][N][k], ...); a single lattice is batch == 1.
+ *
+ * Graph layout (ELL, width k): nbr[N][k] neighbour column ascending, -1 padded on the
+ * right; A[N][k] capped adjacency weights (graph.py:77-83); W[N][k] normalised weights
+ * A_ij/(sd_i*sd_j) (graph.py:87-90); deg[N]; sqrt_deg[N].
+ */
+#ifndef OSCILLINK_B200_H
+#define OSCILLINK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSC_OK 0
+#define OSC_ERR_INVALID 1     /* bad argument (maps to Python ValueError) */
+#define OSC_ERR_CUDA 2        /* CUDA runtime / launch failure */
+#define OSC_ERR_WORKSPACE 3   /* workspace too small */
+#define OSC_ERR_UNSUPPORTED 4 /* shape outside what the kernels cover */
+
+#define OSC_ABI_VERSION 1
+
+/* kNN engine selector for osc_knn_candidates (flags bits 0-1) */
+#define OSC_KNN_AUTO 0
+#define OSC_KNN_SIMT 1 /* fp32 CUDA-core tile kernel (any shape) */
+#define OSC_KNN_TC 2   /* tcgen05 3xTF32 tensor-core kernel (sm_100a) */
+
+/* solve modes for osc_pcg_* / osc_batched_* */
+#define OSC_MODE_SETTLE 0     /* (I + dt M) X = U + dt RHS   lattice.py:170-192 */
+#define OSC_MODE_STATIONARY 1 /* M X = RHS, x0 = Y           lattice.py:245-259 */
+
+typedef struct osc_graph {
+  int64_t batch;
+  int64_t N;
+  int32_t k;
+  int32_t _pad;
+  const int32_t* nbr;
+  const float* A;
+  const float* W;
+  const int32_t* deg;
+  const float* sqrt_deg;
+} osc_graph_t;
+
+/* Chain prior (graph.py:96-111, lattice.py:129-149), CSR over the distinct chain nodes.
+ * n_rows == 0 or a NULL osc_chain_t* means "no chain".  slot[N] maps a lattice row to its
+ * index in rows[] (or -1).  Only valid for batch == 1. */
+typedef struct osc_chain {
+  int32_t n_rows;
+  int32_t nnz;
+  const int32_t* rows;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* Wp; /* Ap_uv/(sdp_u*sdp_v) */
+  const float* Ap; /* raw max-merged path weights */
+  const int32_t* slot;
+} osc_chain_t;
+
+/* lambda parameters; chain_present mirrors `L_path is not None` (lattice.py:180,190):
+ * the operator gets the lamP term only if chain_present && lamP > 0, the Jacobi diagonal
+ * gets +lamP whenever chain_present. */
+typedef struct osc_params {
+  float lamG, lamC, lamQ, lamP;
+  int32_t chain_present;
+  int32_t _pad;
+} osc_params_t;
+
+/* ------------------------------------------------------------------ misc */
+int osc_abi_version(void);
+const char* osc_last_error(void);
+/* sm count, shared memory per block (opt-in), compute capability major*10+minor */
+int osc_device_info(int device, int* h_sm_count, int* h_smem_optin, int* h_cc);
+
+/* ------------------------------------------------------------------ K1: kNN build
+ * Replaces oscillink/core/graph.py:29-62 (normalise, S = Yn Yn^T, diag = -inf, top-k). */
+
+/* Yn = Y / (||Y||_2 + 1e-12) row-wise (graph.py:35).  Yn_hi/Yn_lo (optional, may be NULL)
+ * receive the TF32 split used by the tensor-core kernel: hi = tf32(Yn), lo = tf32(Yn - hi). */
+int osc_normalize_rows(const float* Y, int64_t rows, int32_t D, float* Yn, float* Yn_hi,
+                       float* Yn_lo, void* stream);
+
+/* Candidate pass.  For each of the `n_rows` query rows (global ids row0..row0+n_rows-1 of
+ * every lattice in the batch) keep the kc best columns of Yn_q . Yn_all^T by (approximate
+ * similarity desc, column asc), self column excluded.  Yn_q may alias Yn_all + row0*D.
+ * cand_idx/cand_sim: [batch][n_rows][kc].  flags: OSC_KNN_*.  The TC engine needs the
+ * hi/lo split arrays (same shapes as Yn_q / Yn_all); the SIMT engine ignores them. */
+int osc_knn_candidates(const float* Yn_q, const float* Yn_all, const float* q_hi, const float* q_lo,
+                       const float* all_hi, const float* all_lo, int64_t batch, int64_t n_rows,
+                       int64_t row0, int64_t N, int32_t D, int32_t kc, int32_t flags,
+                       int32_t* cand_idx, float* cand_sim, void* workspace, size_t ws_bytes,
+                       void* stream);
+/* 1 if the tcgen05 engine covers (N, D, kc) on the current device */
+int osc_knn_tc_supported(int64_t N, int32_t D, int32_t kc);
+int osc_knn_candidates_workspace(int64_t batch, int64_t n_rows, int64_t N, int32_t D, int32_t kc,
+                                 int32_t flags, size_t* h_bytes);
+
+/* Canonical ranking (graph.py:46-52): re-score every candidate with an fp64-accumulated dot
+ * of the fp32 rows, round once to fp32, order by (similarity desc, column asc), keep k.
+ * top_idx/top_sim: [batch][n_rows][k].  gap (optional): k-th minus (k+1)-th similarity. */
+int osc_knn_rescore(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows, int64_t N,
+                    int32_t D, const int32_t* cand_idx, int32_t kc, int32_t k, int32_t* top_idx,
+                    float* top_sim, float* gap, void* stream);
+
+/* K1b -- graph.py:50-52 (S>0 filter), :64-65 (mutual), :77-83 (row cap), :87-92 (degree,
+ * normalised weights).  top_idx/top_sim are the directed lists of ALL N rows of each lattice.
+ * scratch: N*batch floats.  nnz: [batch] int64 (device). */
+int osc_graph_assemble(const int32_t* top_idx, const float* top_sim, int64_t batch, int64_t N,
+                       int32_t k, float row_cap, int32_t* nbr, float* A, float* W, int32_t* deg,
+                       float* sqrt_deg, int64_t* nnz, float* scratch, void* stream);
+
+/* Whole build for `batch` lattices resident on one GPU (normalise + candidates + rescore +
+ * assemble).  flags: OSC_KNN_*.  h_near_ties (optional): rows whose k/(k+1) gap < 4e-7. */
+int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int32_t flags,
+                            size_t* h_bytes);
+int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k, float row_cap,
+                  int32_t flags, int32_t* nbr, float* A, float* W, int32_t* deg, float* sqrt_deg,
+                  int64_t* nnz, float* gap, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K2: PCG (single lattice)
+ * Replaces lattice.py:170-207 / :245-265 driving solver.py:15-37.
+ * Phase entry points are exported so a multi-GPU driver can put NCCL all-reduces between
+ * them; osc_pcg_solve composes them on one GPU.
+ *
+ * Sharded use: the local rows are [row0, row0+n_local); vectors passed as `*_all` are
+ * indexed by GLOBAL row (N rows), vectors passed as `*_loc` by local row.  On one GPU
+ * row0 = 0, n_local = N and both views coincide.  graph arrays are LOCAL rows with
+ * GLOBAL neighbour ids. */
+typedef struct osc_pcg_dims {
+  int64_t N;       /* global rows */
+  int64_t row0;    /* first local row */
+  int64_t n_local; /* local rows */
+  int32_t D;
+  int32_t n_blocks; /* row blocks used for the partial sums (from osc_pcg_plan) */
+} osc_pcg_dims_t;
+
+/* fills dims->n_blocks and reports the workspace bytes osc_pcg_solve needs */
+int osc_pcg_plan(osc_pcg_dims_t* dims, size_t* h_ws_bytes);
+
+/* x0 (lattice.py:751-758) and right-hand side (lattice.py:171,184 / :245):
+ * X_loc = Y | U | (1-w)Y + wU ; Bv_loc = U + dt*(lamG*Y + lamQ*b*psi^T)  (settle)
+ *                               Bv_loc = lamG*Y + lamQ*b*psi^T            (stationary) */
+int osc_pcg_setup(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                  int32_t warm_start, float inertia, const float* Y_loc, const float* U_loc,
+                  const float* psi, const float* gates_loc, float* X_loc, float* Bv_loc,
+                  void* stream);
+
+/* R = Bv - Aop(X); P = R/(Mdiag+1e-12) (or R); partial rz.  X_all is the gathered x0. */
+int osc_pcg_residual0(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                      const osc_params_t* prm, int32_t mode, float dt, int32_t jacobi,
+                      const float* gates_loc, const float* X_all, float* RBv_loc, float* P_loc,
+                      double* part_rz, void* stream);
+
+/* AP = Aop(P), partial pAp (solver.py:24-25).  P_all indexed by global row. */
+int osc_pcg_spmm_dot(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                     const osc_params_t* prm, int32_t mode, float dt, const float* gates_loc,
+                     const float* P_all, float* AP_loc, double* part_pap, void* stream);
+
+/* column reduction of the row-block partials: out[D] (fp32) = sum_blocks part[b][D];
+ * if h_or_d_max != NULL also writes max_c sqrt(out[c]) to *d_max (device float). */
+int osc_pcg_reduce(const double* part, int32_t n_blocks, int32_t D, float* out, float* d_max,
+                   void* stream);
+
+/* x += alpha p; r -= alpha Ap; partial rr, partial rz' (solver.py:26-28,32-33);
+ * alpha_c = rz_c/(pap_c + 1e-18) */
+int osc_pcg_update(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                   int32_t jacobi, const float* gates_loc, const float* rz, const float* pap,
+                   const float* P_loc, const float* AP_loc, float* X_loc, float* R_loc,
+                   double* part_rr, double* part_rz, void* stream);
+
+/* p = z + beta p, beta_c = rz_new_c/(rz_old_c + 1e-18) (solver.py:34-35) */
+int osc_pcg_pupdate(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                    int32_t jacobi, const float* gates_loc, const float* rz_new, const float* rz_old,
+                    const float* R_loc, float* P_loc, void* stream);
+
+/* Full single-GPU solve.  X receives the solution ([N][D]); *h_iters / *h_res the
+ * iteration count and last max-column residual (never fails on non-convergence). */
+int osc_pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm,
+                  int32_t mode, float dt, int32_t warm_start, float inertia, int32_t jacobi,
+                  double tol, int32_t max_iters, const float* Y, const float* U, const float* psi,
+                  const float* gates, int32_t D, float* X, int32_t* h_iters, float* h_res,
+                  void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K4: receipts
+ * deltaH = <U-U*, M (U-U*)>  (receipts.py:21-25).  workspace from osc_pcg_plan. */
+int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm,
+                const float* U, const float* Ustar, const float* gates, int32_t D,
+                double* h_deltaH, void* workspace, size_t ws_bytes, void* stream);
+
+/* Per-node terms (receipts.py:40-59) and null points (receipts.py:70-82), one pass.
+ * coh/anchor/query: [N]; null_j[N] (-1 = none), null_z[N], null_R[N]. */
+int osc_receipt_full(const osc_graph_t* g, const osc_params_t* prm, const float* Y,
+                     const float* Ustar, const float* psi, const float* gates, int32_t D, float z_th,
+                     float* coh, float* anchor, float* query, int32_t* null_j, float* null_z,
+                     float* null_R, void* stream);
+
+/* ------------------------------------------------------------------ K3: batched serving
+ * One persistent kernel settles `batch` independent lattices of equal (N, D, k):
+ * each CTA owns an 8-column slab of one lattice with the CG vectors in registers/shared
+ * memory.  do_settle: U_out = settle(U_in or Y).  do_ustar: Ustar_out = stationary solve.
+ * do_deltaH: deltaH[b] = <U_out - Ustar, M (U_out - Ustar)> (needs both).
+ * psi: [batch][D]; gates: [batch][N] or NULL (= ones).  stats: [batch][4] floats
+ * {settle_iters, settle_res, ustar_iters, ustar_res}.  sync_ws: zero-initialised by the
+ * call; size from osc_batched_workspace. */
+typedef struct osc_batched_args {
+  const float* Y;
+  const float* U_in; /* NULL -> Y */
+  const float* psi;
+  const float* gates; /* NULL -> ones */
+  float* U_out;
+  float* Ustar_out; /* may be NULL unless do_ustar output is wanted */
+  float* stats;
+  double* deltaH; /* [batch] */
+  int32_t D;
+  int32_t do_settle, do_ustar, do_deltaH;
+  float dt;
+  double tol_settle, tol_ustar;
+  int32_t max_iters_settle, max_iters_ustar;
+} osc_batched_args_t;
+
+int osc_batched_supported(int64_t N, int32_t D, int32_t k);
+int osc_batched_workspace(int64_t batch, int64_t N, int32_t D, size_t* h_bytes);
+int osc_batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batched_args_t* a,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSCILLINK_B200_H */

@@ -1,0 +1,189 @@
+"""Serving-batch API: many independent lattices of equal shape on one B200.
+
+BASELINE.json config "serving batch: 4096 independent lattices N=1200 D=384 settled
+concurrently".  Semantically each lattice b is exactly
+
+    lat = OscillinkLattice(Y[b], kneighbors=k, deterministic_k=True, ...)
+    lat.set_query(psi[b], gates[b]); lat.settle(...); lat.set_receipt_detail("light"); lat.receipt()
+
+(the cloud handler's per-request sequence, cloud/app/main.py:916-939,1043,1061) but the whole
+batch is built by one fused kNN pass and settled by ONE persistent kernel
+(osc_batched_settle, csrc/batched.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import BatchedArgs, Graph, Params
+
+__all__ = ["BatchedLattices"]
+
+
+class BatchedLattices:
+    def __init__(self, Y, kneighbors: int = 6, row_cap_val: float = 1.0, lamG: float = 1.0,
+                 lamC: float = 0.5, lamQ: float = 4.0, *, knn_engine: int = _cabi.KNN_AUTO,
+                 device: torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("oscillink_b200 needs a CUDA device (sm_100a); no CPU fallback")
+        if kneighbors < 1:
+            raise ValueError("kneighbors must be >= 1")
+        if lamG <= 0:
+            raise ValueError("lamG must be > 0 for SPD")
+        if lamC < 0 or lamQ < 0:
+            raise ValueError("lamC and lamQ must be >= 0")
+        self._dev = device or torch.device("cuda", torch.cuda.current_device())
+        self._lib = _cabi.load()
+        if isinstance(Y, np.ndarray):
+            if Y.ndim != 3:
+                raise ValueError("Y must be a (batch, N, D) array")
+            Y = torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float32)).to(self._dev, non_blocking=True)
+        if Y.ndim != 3 or Y.dtype != torch.float32 or not Y.is_cuda:
+            raise ValueError("Y must be a (batch, N, D) float32 array / CUDA tensor")
+        self.Y = Y.contiguous()
+        self.B, self.N, self.D = (int(s) for s in self.Y.shape)
+        self.k = min(int(kneighbors), max(1, self.N - 1))
+        self.row_cap_val = float(row_cap_val)
+        self.lamG, self.lamC, self.lamQ = float(lamG), float(lamC), float(lamQ)
+        self._engine = knn_engine
+        self._ws = None
+        self.psi = torch.zeros((self.B, self.D), dtype=torch.float32, device=self._dev)
+        self.gates = None
+        self.U = None
+        self.Ustar = None
+        self._build()
+
+    def _workspace(self, nbytes: int):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self._dev)
+        return self._ws
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def _build(self) -> None:
+        """graph.py:29-93 for the whole batch, composed from the exported K1/K1b phases so each
+        phase can be timed with CUDA events on the launching stream (bench.py roofline)."""
+        B, N, D, k, dev, lib = self.B, self.N, self.D, self.k, self._dev, self._lib
+        self.nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+        self.A = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+        self.W = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+        self.deg = torch.empty((B, N), dtype=torch.int32, device=dev)
+        self.sqrt_deg = torch.empty((B, N), dtype=torch.float32, device=dev)
+        self.nnz = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.gap = torch.empty((B, N), dtype=torch.float32, device=dev)
+        self.events = {}
+        if N < 2:
+            need = C.c_size_t(0)
+            _cabi.check(lib.osc_knn_build_workspace(B, N, D, k, self._engine, C.byref(need)))
+            ws = self._workspace(need.value)
+            _cabi.check(lib.osc_knn_build(self.Y.data_ptr(), B, N, D, k, self.row_cap_val, self._engine,
+                                          self.nbr.data_ptr(), self.A.data_ptr(), self.W.data_ptr(),
+                                          self.deg.data_ptr(), self.sqrt_deg.data_ptr(),
+                                          self.nnz.data_ptr(), self.gap.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), self._stream()), "osc_knn_build")
+            return
+        kc = min(k + 4, N - 1)
+        rows = B * N
+        use_tc = self._engine != _cabi.KNN_SIMT and bool(lib.osc_knn_tc_supported(N, D, kc))
+        if self._engine == _cabi.KNN_TC and not use_tc:
+            raise _cabi.OscillinkNativeError("tensor-core kNN engine does not cover this shape")
+        self.engine_used = "tc" if use_tc else "simt"
+        Yn = torch.empty_like(self.Y)
+        hi = torch.empty_like(self.Y) if use_tc else None
+        lo = torch.empty_like(self.Y) if use_tc else None
+        cand_idx = torch.empty((B, N, kc), dtype=torch.int32, device=dev)
+        cand_sim = torch.empty((B, N, kc), dtype=torch.float32, device=dev)
+        top_idx = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+        top_sim = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+        scratch = torch.empty(rows, dtype=torch.float32, device=dev)
+        st = self._stream()
+
+        def phase(name, rc_fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _cabi.check(rc_fn(), name)
+            e1.record()
+            self.events[name] = (e0, e1)
+
+        P = _cabi.ptr
+        phase("normalize", lambda: lib.osc_normalize_rows(self.Y.data_ptr(), rows, D, Yn.data_ptr(),
+                                                          P(hi), P(lo), st))
+        phase("knn_candidates", lambda: lib.osc_knn_candidates(
+            Yn.data_ptr(), Yn.data_ptr(), P(hi), P(lo), P(hi), P(lo), B, N, 0, N, D, kc,
+            _cabi.KNN_TC if use_tc else _cabi.KNN_SIMT, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st))
+        phase("knn_rescore", lambda: lib.osc_knn_rescore(
+            Yn.data_ptr(), Yn.data_ptr(), B, N, N, D, cand_idx.data_ptr(), kc, k, top_idx.data_ptr(),
+            top_sim.data_ptr(), self.gap.data_ptr(), st))
+        phase("graph_assemble", lambda: lib.osc_graph_assemble(
+            top_idx.data_ptr(), top_sim.data_ptr(), B, N, k, self.row_cap_val, self.nbr.data_ptr(),
+            self.A.data_ptr(), self.W.data_ptr(), self.deg.data_ptr(), self.sqrt_deg.data_ptr(),
+            self.nnz.data_ptr(), scratch.data_ptr(), st))
+
+    def phase_ms(self) -> dict:
+        """Device time of every recorded phase (synchronises)."""
+        torch.cuda.current_stream().synchronize()
+        return {k: e0.elapsed_time(e1) for k, (e0, e1) in self.events.items()}
+
+    def set_query(self, psi, gates=None) -> None:
+        psi_t = torch.as_tensor(psi, dtype=torch.float32)
+        if psi_t.ndim == 1:
+            psi_t = psi_t.expand(self.B, self.D)
+        if tuple(psi_t.shape) != (self.B, self.D):
+            raise ValueError("psi must be (D,) or (batch, D)")
+        self.psi = psi_t.to(self._dev, non_blocking=True).contiguous()
+        if gates is not None:
+            g = torch.as_tensor(gates, dtype=torch.float32)
+            if tuple(g.shape) != (self.B, self.N):
+                raise ValueError("gates length mismatch N")
+            self.gates = g.to(self._dev, non_blocking=True).contiguous()
+
+    def supported(self) -> bool:
+        return bool(self._lib.osc_batched_supported(self.N, self.D, self.k))
+
+    def settle(self, dt: float = 1.0, max_iters: int = 12, tol: float = 1e-3, *, receipt: bool = True,
+               ustar_tol: float = 1e-4, ustar_max_iters: int = 64, keep_ustar: bool = False
+               ) -> dict[str, Any]:
+        """settle() [+ light receipt()] for every lattice, one persistent kernel launch.
+
+        Returns device tensors: iters[B], res[B] and, with receipt=True, ustar_iters[B],
+        ustar_res[B], deltaH[B] (float64)."""
+        if not self.supported():
+            raise _cabi.OscillinkNativeError(
+                "batched kernel does not cover this shape; use OscillinkLattice per lattice")
+        B, dev = self.B, self._dev
+        U_in = self.U
+        U_out = torch.empty_like(self.Y)
+        stats = torch.zeros((B, 4), dtype=torch.float32, device=dev)
+        dH = torch.zeros(B, dtype=torch.float64, device=dev)
+        Us = torch.empty_like(self.Y) if (receipt and keep_ustar) else None
+        g = Graph(B, self.N, self.k, 0, self.nbr.data_ptr(), self.A.data_ptr(), self.W.data_ptr(),
+                  self.deg.data_ptr(), self.sqrt_deg.data_ptr())
+        prm = Params(self.lamG, self.lamC, self.lamQ, 0.0, 0, 0)
+        args = BatchedArgs(self.Y.data_ptr(), _cabi.ptr(U_in), self.psi.data_ptr(), _cabi.ptr(self.gates),
+                           U_out.data_ptr(), _cabi.ptr(Us), stats.data_ptr(), dH.data_ptr(), self.D,
+                           1, 1 if receipt else 0, 1 if receipt else 0, float(dt), float(tol),
+                           float(ustar_tol), int(max_iters), int(ustar_max_iters))
+        need = C.c_size_t(0)
+        _cabi.check(self._lib.osc_batched_workspace(B, self.N, self.D, C.byref(need)))
+        ws = self._workspace(need.value)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _cabi.check(
+            self._lib.osc_batched_settle(C.byref(g), C.byref(prm), C.byref(args), ws.data_ptr(),
+                                         ws.numel(), self._stream()),
+            "osc_batched_settle",
+        )
+        e1.record()
+        self.events["batched_settle"] = (e0, e1)
+        self.U = U_out
+        self.Ustar = Us
+        out = {"iters": stats[:, 0], "res": stats[:, 1]}
+        if receipt:
+            out.update({"ustar_iters": stats[:, 2], "ustar_res": stats[:, 3], "deltaH": dH})
+        return out

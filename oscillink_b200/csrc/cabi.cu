@@ -1,0 +1,326 @@
+// extern "C" surface declared in include/oscillink_b200.h.  No exceptions cross this boundary:
+// every entry point returns a status code and records the failure text per host thread.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace osc {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return OSC_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// launchers implemented in the kernel translation units
+int launch_normalize(const float*, int64_t, int, float*, float*, float*, cudaStream_t);
+int launch_knn_simt(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, int, int32_t*,
+                    float*, cudaStream_t);
+int knn_tc_supported(int64_t N, int D, int kc);
+int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
+                  int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
+                  int32_t* cand_idx, float* cand_sim, cudaStream_t st);
+int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int, int,
+                   int32_t*, float*, float*, cudaStream_t);
+int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
+                    int32_t*, float*, int64_t*, float*, cudaStream_t);
+int pcg_plan(osc_pcg_dims_t*, size_t*);
+int pcg_setup(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, float, const float*,
+              const float*, const float*, const float*, float*, float*, cudaStream_t);
+int pcg_residual0(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
+                  int, float, int, const float*, const float*, float*, float*, double*, cudaStream_t);
+int pcg_spmm_dot(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
+                 int, float, const float*, const float*, float*, double*, cudaStream_t);
+int pcg_reduce(const double*, int, int, float*, float*, double*, cudaStream_t);
+int pcg_update(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, const float*, const float*,
+               const float*, const float*, const float*, float*, float*, double*, double*,
+               cudaStream_t);
+int pcg_pupdate(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, const float*,
+                const float*, const float*, const float*, float*, cudaStream_t);
+int pcg_solve(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, int, float, int, float, int,
+              double, int, const float*, const float*, const float*, const float*, int, float*, int*,
+              float*, void*, size_t, cudaStream_t);
+int delta_h(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, const float*, const float*,
+            const float*, int, double*, void*, size_t, cudaStream_t);
+int launch_receipt_full(const osc_graph_t*, const osc_params_t*, const float*, const float*,
+                        const float*, const float*, int, float, float*, float*, float*, int32_t*,
+                        float*, float*, cudaStream_t);
+int batched_supported(int64_t, int, int);
+int batched_workspace(int64_t, int64_t, int, size_t*);
+int batched_settle(const osc_graph_t*, const osc_params_t*, const osc_batched_args_t*, void*, size_t,
+                   cudaStream_t);
+
+static int candidate_width(int64_t N, int k) {
+  // k + 4 spare candidates so that 3xTF32 / fp32 rounding noise (~1e-7) cannot push a true
+  // top-k column out of the candidate list (DESIGN.md "near-ties")
+  int64_t kc = (int64_t)k + 4;
+  if (kc > N - 1) kc = N - 1;
+  if (kc < 1) kc = 1;
+  return (int)kc;
+}
+
+static int pick_engine(int flags, int64_t N, int D, int kc) {
+  const int want = flags & 3;
+  if (want == OSC_KNN_SIMT) return OSC_KNN_SIMT;
+  if (knn_tc_supported(N, D, kc)) return OSC_KNN_TC;
+  return (want == OSC_KNN_TC) ? -1 : OSC_KNN_SIMT;
+}
+
+}  // namespace osc
+
+using namespace osc;
+
+extern "C" {
+
+int osc_abi_version(void) { return OSC_ABI_VERSION; }
+const char* osc_last_error(void) { return g_last_error.c_str(); }
+
+int osc_device_info(int device, int* h_sm_count, int* h_smem_optin, int* h_cc) {
+  int n = 0, s = 0, mj = 0, mn = 0;
+  OSC_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  OSC_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  OSC_CUDA(cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, device));
+  OSC_CUDA(cudaDeviceGetAttribute(&mn, cudaDevAttrComputeCapabilityMinor, device));
+  if (h_sm_count) *h_sm_count = n;
+  if (h_smem_optin) *h_smem_optin = s;
+  if (h_cc) *h_cc = mj * 10 + mn;
+  return OSC_OK;
+}
+
+int osc_normalize_rows(const float* Y, int64_t rows, int32_t D, float* Yn, float* Yn_hi, float* Yn_lo,
+                       void* stream) {
+  OSC_REQUIRE(Y != nullptr && Yn != nullptr && rows >= 0 && D >= 1, "normalize_rows: bad argument");
+  OSC_REQUIRE((Yn_hi == nullptr) == (Yn_lo == nullptr), "normalize_rows: hi/lo must come together");
+  return launch_normalize(Y, rows, D, Yn, Yn_hi, Yn_lo, (cudaStream_t)stream);
+}
+
+int osc_knn_tc_supported(int64_t N, int32_t D, int32_t kc) { return knn_tc_supported(N, D, kc); }
+
+int osc_knn_candidates_workspace(int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, size_t* h_bytes) {
+  if (h_bytes) *h_bytes = 256;
+  return OSC_OK;
+}
+
+int osc_knn_candidates(const float* Yn_q, const float* Yn_all, const float* q_hi, const float* q_lo,
+                       const float* all_hi, const float* all_lo, int64_t batch, int64_t n_rows,
+                       int64_t row0, int64_t N, int32_t D, int32_t kc, int32_t flags,
+                       int32_t* cand_idx, float* cand_sim, void*, size_t, void* stream) {
+  OSC_REQUIRE(batch >= 0 && n_rows >= 0 && N >= 2 && D >= 1, "knn_candidates: bad shape");
+  OSC_REQUIRE(kc >= 1 && kc <= N - 1 && kc <= 132, "knn_candidates: kc must be in [1, min(N-1,132)]");
+  OSC_REQUIRE(batch <= 65535, "knn_candidates: batch > 65535 (split the batch)");
+  OSC_REQUIRE(cand_idx != nullptr && cand_sim != nullptr, "knn_candidates: NULL output");
+  if (batch == 0 || n_rows == 0) return OSC_OK;
+  const int eng = pick_engine(flags, N, D, kc);
+  if (eng < 0) return fail(OSC_ERR_UNSUPPORTED, "knn_candidates: tensor-core engine does not cover this shape");
+  if (eng == OSC_KNN_TC) {
+    OSC_REQUIRE(q_hi && q_lo && all_hi && all_lo, "knn_candidates: TC engine needs the hi/lo split");
+    return launch_knn_tc(q_hi, q_lo, all_hi, all_lo, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
+                         (cudaStream_t)stream);
+  }
+  OSC_REQUIRE(Yn_q != nullptr && Yn_all != nullptr, "knn_candidates: NULL input");
+  return launch_knn_simt(Yn_q, Yn_all, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
+                         (cudaStream_t)stream);
+}
+
+int osc_knn_rescore(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows, int64_t N,
+                    int32_t D, const int32_t* cand_idx, int32_t kc, int32_t k, int32_t* top_idx,
+                    float* top_sim, float* gap, void* stream) {
+  OSC_REQUIRE(Yn_q && Yn_all && cand_idx && top_idx && top_sim, "knn_rescore: NULL argument");
+  OSC_REQUIRE(k >= 1 && kc >= k && batch <= 65535, "knn_rescore: need 1 <= k <= kc");
+  if (batch == 0 || n_rows == 0) return OSC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * batch * n_rows * k, st));
+  OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * batch * n_rows * k, st));
+  return launch_rescore(Yn_q, Yn_all, batch, n_rows, N, D, cand_idx, kc, k, top_idx, top_sim, gap, st);
+}
+
+int osc_graph_assemble(const int32_t* top_idx, const float* top_sim, int64_t batch, int64_t N, int32_t k,
+                       float row_cap, int32_t* nbr, float* A, float* W, int32_t* deg, float* sqrt_deg,
+                       int64_t* nnz, float* scratch, void* stream) {
+  OSC_REQUIRE(top_idx && top_sim && nbr && A && W && deg && sqrt_deg && scratch,
+              "graph_assemble: NULL argument");
+  OSC_REQUIRE(k >= 1 && batch <= 65535, "graph_assemble: bad k/batch");
+  return launch_assemble(top_idx, top_sim, batch, N, k, row_cap, nbr, A, W, deg, sqrt_deg, nnz, scratch,
+                         (cudaStream_t)stream);
+}
+
+int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int32_t flags,
+                            size_t* h_bytes) {
+  OSC_REQUIRE(h_bytes != nullptr && batch >= 0 && N >= 0 && D >= 1 && k >= 1, "knn_build_workspace: bad argument");
+  if (N < 2) {
+    *h_bytes = 256;
+    return OSC_OK;
+  }
+  const int kc = candidate_width(N, k);
+  const int eng = pick_engine(flags, N, D, kc);
+  const size_t rows = (size_t)batch * N;
+  size_t b = align_up(rows * D * sizeof(float));                      // Yn
+  if (eng == OSC_KNN_TC) b += 2 * align_up(rows * D * sizeof(float));  // hi, lo
+  b += align_up(rows * kc * sizeof(int32_t)) + align_up(rows * kc * sizeof(float));  // candidates
+  b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
+  b += align_up(rows * sizeof(float));                                               // cap scale
+  *h_bytes = b + 1024;
+  return OSC_OK;
+}
+
+int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k, float row_cap,
+                  int32_t flags, int32_t* nbr, float* A, float* W, int32_t* deg, float* sqrt_deg,
+                  int64_t* nnz, float* gap, void* workspace, size_t ws_bytes, void* stream) {
+  OSC_REQUIRE(Y && nbr && A && W && deg && sqrt_deg, "knn_build: NULL argument");
+  OSC_REQUIRE(batch >= 0 && N >= 0 && D >= 1 && k >= 1, "knn_build: bad shape");
+  OSC_REQUIRE(batch <= 65535, "knn_build: batch > 65535 (split the batch)");
+  OSC_REQUIRE(k <= 128, "knn_build: kneighbors > 128 is not supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rows = (size_t)batch * N;
+  if (rows == 0) return OSC_OK;
+  if (N < 2) {
+    // graph.py:30-32 -- no neighbours possible; sqrt_deg = sqrt(1e-12)
+    OSC_CUDA(cudaMemsetAsync(nbr, 0xFF, rows * k * sizeof(int32_t), st));
+    OSC_CUDA(cudaMemsetAsync(A, 0, rows * k * sizeof(float), st));
+    OSC_CUDA(cudaMemsetAsync(W, 0, rows * k * sizeof(float), st));
+    OSC_CUDA(cudaMemsetAsync(deg, 0, rows * sizeof(int32_t), st));
+    if (nnz) OSC_CUDA(cudaMemsetAsync(nnz, 0, batch * sizeof(int64_t), st));
+    std::vector<float> sd(rows, 1e-6f);
+    OSC_CUDA(cudaMemcpyAsync(sqrt_deg, sd.data(), rows * sizeof(float), cudaMemcpyHostToDevice, st));
+    OSC_CUDA(cudaStreamSynchronize(st));
+    return OSC_OK;
+  }
+  OSC_REQUIRE(k <= N - 1, "knn_build: k must be clamped to N-1 by the caller (lattice.py:60)");
+  size_t need = 0;
+  int rc = osc_knn_build_workspace(batch, N, D, k, flags, &need);
+  if (rc) return rc;
+  if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
+  const int kc = candidate_width(N, k);
+  const int eng = pick_engine(flags, N, D, kc);
+  if (eng < 0) return fail(OSC_ERR_UNSUPPORTED, "knn_build: tensor-core engine does not cover this shape");
+  Arena ar(workspace, ws_bytes);
+  float* Yn = ar.take<float>(rows * D);
+  float *hi = nullptr, *lo = nullptr;
+  if (eng == OSC_KNN_TC) {
+    hi = ar.take<float>(rows * D);
+    lo = ar.take<float>(rows * D);
+  }
+  int32_t* cand_idx = ar.take<int32_t>(rows * kc);
+  float* cand_sim = ar.take<float>(rows * kc);
+  int32_t* top_idx = ar.take<int32_t>(rows * k);
+  float* top_sim = ar.take<float>(rows * k);
+  float* cscale = ar.take<float>(rows);
+  if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
+  if ((rc = launch_normalize(Y, (int64_t)rows, D, Yn, hi, lo, st))) return rc;
+  if ((rc = osc_knn_candidates(Yn, Yn, hi, lo, hi, lo, batch, N, 0, N, D, kc, eng, cand_idx, cand_sim,
+                               nullptr, 0, stream)))
+    return rc;
+  if ((rc = osc_knn_rescore(Yn, Yn, batch, N, N, D, cand_idx, kc, k, top_idx, top_sim, gap, stream)))
+    return rc;
+  return launch_assemble(top_idx, top_sim, batch, N, k, row_cap, nbr, A, W, deg, sqrt_deg, nnz, cscale, st);
+}
+
+// ------------------------------------------------------------------ PCG
+int osc_pcg_plan(osc_pcg_dims_t* dims, size_t* h_ws_bytes) { return pcg_plan(dims, h_ws_bytes); }
+
+int osc_pcg_setup(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                  int32_t warm_start, float inertia, const float* Y_loc, const float* U_loc,
+                  const float* psi, const float* gates_loc, float* X_loc, float* Bv_loc, void* stream) {
+  OSC_REQUIRE(dims && prm && Y_loc && U_loc && psi && X_loc && Bv_loc, "pcg_setup: NULL argument");
+  return pcg_setup(dims, prm, mode, dt, warm_start, inertia, Y_loc, U_loc, psi, gates_loc, X_loc, Bv_loc,
+                   (cudaStream_t)stream);
+}
+
+int osc_pcg_residual0(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                      const osc_params_t* prm, int32_t mode, float dt, int32_t jacobi,
+                      const float* gates_loc, const float* X_all, float* RBv_loc, float* P_loc,
+                      double* part_rz, void* stream) {
+  OSC_REQUIRE(dims && g && prm && X_all && RBv_loc && P_loc && part_rz, "pcg_residual0: NULL argument");
+  return pcg_residual0(dims, g, chain, prm, mode, dt, jacobi, gates_loc, X_all, RBv_loc, P_loc, part_rz,
+                       (cudaStream_t)stream);
+}
+
+int osc_pcg_spmm_dot(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                     const osc_params_t* prm, int32_t mode, float dt, const float* gates_loc,
+                     const float* P_all, float* AP_loc, double* part_pap, void* stream) {
+  OSC_REQUIRE(dims && g && prm && P_all && AP_loc && part_pap, "pcg_spmm_dot: NULL argument");
+  return pcg_spmm_dot(dims, g, chain, prm, mode, dt, gates_loc, P_all, AP_loc, part_pap,
+                      (cudaStream_t)stream);
+}
+
+int osc_pcg_reduce(const double* part, int32_t n_blocks, int32_t D, float* out, float* d_max,
+                   void* stream) {
+  OSC_REQUIRE(part && out && n_blocks >= 1 && D >= 1, "pcg_reduce: bad argument");
+  return pcg_reduce(part, n_blocks, D, out, d_max, nullptr, (cudaStream_t)stream);
+}
+
+int osc_pcg_update(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                   int32_t jacobi, const float* gates_loc, const float* rz, const float* pap,
+                   const float* P_loc, const float* AP_loc, float* X_loc, float* R_loc,
+                   double* part_rr, double* part_rz, void* stream) {
+  OSC_REQUIRE(dims && prm && rz && pap && P_loc && AP_loc && X_loc && R_loc && part_rr && part_rz,
+              "pcg_update: NULL argument");
+  return pcg_update(dims, prm, mode, dt, jacobi, gates_loc, rz, pap, P_loc, AP_loc, X_loc, R_loc,
+                    part_rr, part_rz, (cudaStream_t)stream);
+}
+
+int osc_pcg_pupdate(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                    int32_t jacobi, const float* gates_loc, const float* rz_new, const float* rz_old,
+                    const float* R_loc, float* P_loc, void* stream) {
+  OSC_REQUIRE(dims && prm && rz_new && rz_old && R_loc && P_loc, "pcg_pupdate: NULL argument");
+  return pcg_pupdate(dims, prm, mode, dt, jacobi, gates_loc, rz_new, rz_old, R_loc, P_loc,
+                     (cudaStream_t)stream);
+}
+
+int osc_pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, int32_t mode,
+                  float dt, int32_t warm_start, float inertia, int32_t jacobi, double tol,
+                  int32_t max_iters, const float* Y, const float* U, const float* psi,
+                  const float* gates, int32_t D, float* X, int32_t* h_iters, float* h_res,
+                  void* workspace, size_t ws_bytes, void* stream) {
+  return pcg_solve(g, chain, prm, mode, dt, warm_start, inertia, jacobi, tol, max_iters, Y, U, psi, gates,
+                   D, X, h_iters, h_res, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, const float* U,
+                const float* Ustar, const float* gates, int32_t D, double* h_deltaH, void* workspace,
+                size_t ws_bytes, void* stream) {
+  return delta_h(g, chain, prm, U, Ustar, gates, D, h_deltaH, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int osc_receipt_full(const osc_graph_t* g, const osc_params_t* prm, const float* Y, const float* Ustar,
+                     const float* psi, const float* gates, int32_t D, float z_th, float* coh,
+                     float* anchor, float* query, int32_t* null_j, float* null_z, float* null_R,
+                     void* stream) {
+  OSC_REQUIRE(coh && anchor && query && null_j && null_z && null_R, "receipt_full: NULL output");
+  return launch_receipt_full(g, prm, Y, Ustar, psi, gates, D, z_th, coh, anchor, query, null_j, null_z,
+                             null_R, (cudaStream_t)stream);
+}
+
+int osc_batched_supported(int64_t N, int32_t D, int32_t k) { return batched_supported(N, D, k); }
+int osc_batched_workspace(int64_t batch, int64_t N, int32_t D, size_t* h_bytes) {
+  OSC_REQUIRE(h_bytes != nullptr, "batched_workspace: NULL");
+  return batched_workspace(batch, N, D, h_bytes);
+}
+int osc_batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batched_args_t* a,
+                       void* workspace, size_t ws_bytes, void* stream) {
+  return batched_settle(g, prm, a, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

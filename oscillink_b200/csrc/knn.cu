@@ -1,0 +1,249 @@
+// K1 (CUDA-core engine) + canonical re-scoring.
+//
+//  normalize_rows_kernel : graph.py:35   Yn = Y / (||Y|| + 1e-12), plus the TF32 hi/lo split
+//  knn_simt_kernel       : graph.py:36-37,59  S = Yn Yn^T (diag excluded) with a fused per-row
+//                          top-kc list kept in shared memory -- the N x N matrix never exists
+//  knn_rescore_kernel    : graph.py:46-52  canonical order (fp32(exact dot) desc, column asc)
+//
+// The tensor-core engine (knn_tc.cu) produces the same candidate lists; both feed
+// knn_rescore_kernel, which is what fixes the final neighbour sets.
+#include "common.cuh"
+
+namespace osc {
+
+// ---------------------------------------------------------------- normalise + TF32 split
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ Y, int64_t rows,
+                                                             int D, float* __restrict__ Yn,
+                                                             float* __restrict__ hi,
+                                                             float* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* y = Y + row * D;
+  double ss = 0.0;
+  for (int d = lane; d < D; d += 32) {
+    double v = (double)y[d];
+    ss = fma(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float den = (float)sqrt(ss) + 1e-12f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = __fdiv_rn(y[d], den);
+    Yn[row * D + d] = v;
+    if (hi != nullptr) {
+      const float h = to_tf32(v);
+      hi[row * D + d] = h;
+      lo[row * D + d] = to_tf32(v - h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- SIMT candidate kernel
+constexpr int TM = 64, TN = 64, BK = 16;
+
+__device__ __forceinline__ void list_insert(float* lv, int* li, int& cnt, int kc, float s, int j) {
+  int p = (cnt < kc) ? cnt : kc - 1;
+  while (p > 0 && lv[p - 1] < s) {  // strict: an equal score keeps the earlier (smaller) column
+    lv[p] = lv[p - 1];
+    li[p] = li[p - 1];
+    --p;
+  }
+  lv[p] = s;
+  li[p] = j;
+  if (cnt < kc) ++cnt;
+}
+
+__global__ void __launch_bounds__(256)
+knn_simt_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, int64_t n_rows,
+                int64_t row0, int64_t N, int D, int kc, int kcp, int32_t* __restrict__ cand_idx,
+                float* __restrict__ cand_sim) {
+  extern __shared__ float smem[];
+  float* As = smem;                 // [BK][TM+1]
+  float* Bs = As + BK * (TM + 1);   // [BK][TN+1]
+  float* Ss = Bs + BK * (TN + 1);   // [TM][TN+1]
+  float* Lv = Ss + TM * (TN + 1);   // [TM][kcp]
+  int* Li = reinterpret_cast<int*>(Lv + TM * kcp);
+
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  const int64_t b = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * TM;  // first query row (panel-local numbering)
+  const float* q = Yq + b * n_rows * D;
+  const float* all = Yall + b * N * D;
+
+  int cnt = 0;  // meaningful for t < TM only
+  const int lm = t >> 2;         // tile row loaded by this thread
+  const int lk = (t & 3) * 4;    // first k offset loaded by this thread
+
+  for (int64_t c0 = 0; c0 < N; c0 += TN) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < D; k0 += BK) {
+      // stage A (query rows) and B (column rows), k-major
+      {
+        const int64_t ra = r0 + lm;
+        const int64_t rb = c0 + lm;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int kk = k0 + lk + u;
+          As[(lk + u) * (TM + 1) + lm] = (ra < n_rows && kk < D) ? q[ra * D + kk] : 0.f;
+          Bs[(lk + u) * (TN + 1) + lm] = (rb < N && kk < D) ? all[rb * D + kk] : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk * (TM + 1) + ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = Bs[kk * (TN + 1) + tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ss[(ty * 4 + i) * (TN + 1) + tx * 4 + j] = acc[i][j];
+    __syncthreads();
+    if (t < TM) {
+      const int64_t gi = row0 + r0 + t;  // global id of this query row
+      if (r0 + t < n_rows) {
+        float* lv = Lv + t * kcp;
+        int* li = Li + t * kcp;
+        const int lim = (int)min((int64_t)TN, N - c0);
+        for (int c = 0; c < lim; ++c) {
+          const int64_t j = c0 + c;
+          if (j == gi) continue;
+          const float s = Ss[t * (TN + 1) + c];
+          if (cnt < kc || s > lv[kc - 1]) list_insert(lv, li, cnt, kc, s, (int)j);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (t < TM && r0 + t < n_rows) {
+    const int64_t o = (b * n_rows + r0 + t) * kc;
+    for (int c = 0; c < kc; ++c) {
+      cand_idx[o + c] = (c < cnt) ? Li[t * kcp + c] : -1;
+      cand_sim[o + c] = (c < cnt) ? Lv[t * kcp + c] : -INFINITY;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- canonical re-scoring
+// One warp per query row.  dynamic smem: warps * kc * (float + int).
+__global__ void __launch_bounds__(256)
+knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, int64_t n_rows,
+                   int64_t N, int D, const int32_t* __restrict__ cand_idx, int kc, int k,
+                   int32_t* __restrict__ top_idx, float* __restrict__ top_sim,
+                   float* __restrict__ gap) {
+  extern __shared__ float smem[];
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sv = smem + (size_t)w * kc;
+  int* sj = reinterpret_cast<int*>(smem + (size_t)warps * kc) + (size_t)w * kc;
+  const int64_t b = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * warps + w;
+  if (r >= n_rows) return;
+  const float* yi = Yq + (b * n_rows + r) * D;
+  const float* all = Yall + b * N * D;
+  const int32_t* ci = cand_idx + (b * n_rows + r) * kc;
+  for (int c = 0; c < kc; ++c) {
+    const int j = ci[c];
+    float s = -INFINITY;
+    if (j >= 0) {
+      const float* yj = all + (int64_t)j * D;
+      double acc = 0.0;
+      for (int d = lane; d < D; d += 32) acc = fma((double)yi[d], (double)yj[d], acc);
+      acc = warp_sum(acc);
+      s = (float)acc;
+    }
+    if (lane == 0) {
+      sv[c] = s;
+      sj[c] = j;
+    }
+  }
+  __syncwarp();
+  const int64_t o = (b * n_rows + r) * k;
+  float kth = INFINITY, nxt = -INFINITY;
+  for (int c = lane; c < kc; c += 32) {
+    const float s = sv[c];
+    const int j = sj[c];
+    if (j < 0) continue;
+    int rank = 0;
+    for (int c2 = 0; c2 < kc; ++c2) {
+      const int j2 = sj[c2];
+      if (j2 >= 0 && c2 != c && better(sv[c2], j2, s, j)) ++rank;
+    }
+    if (rank < k) {
+      top_idx[o + rank] = j;
+      top_sim[o + rank] = s;
+    }
+    if (rank == k - 1) kth = s;
+    if (rank == k) nxt = s;
+  }
+  if (gap != nullptr) {
+    // exactly one lane holds each of kth / nxt
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
+      nxt = fmaxf(nxt, __shfl_xor_sync(0xffffffffu, nxt, off));
+    }
+    if (lane == 0) gap[b * n_rows + r] = (nxt == -INFINITY) ? INFINITY : kth - nxt;
+  }
+}
+
+// ---------------------------------------------------------------- host launchers
+int launch_normalize(const float* Y, int64_t rows, int D, float* Yn, float* hi, float* lo,
+                     cudaStream_t st) {
+  if (rows == 0) return OSC_OK;
+  const int warps = 8;
+  const int64_t blocks = (rows + warps - 1) / warps;
+  normalize_rows_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(Y, rows, D, Yn, hi, lo);
+  OSC_LAUNCH_CHECK("normalize_rows_kernel");
+  return OSC_OK;
+}
+
+int launch_knn_simt(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t row0,
+                    int64_t N, int D, int kc, int32_t* cand_idx, float* cand_sim, cudaStream_t st) {
+  const int kcp = kc | 1;
+  const size_t smem = sizeof(float) * (BK * (TM + 1) + BK * (TN + 1) + TM * (TN + 1)) +
+                      (size_t)TM * kcp * (sizeof(float) + sizeof(int));
+  if (smem > 48 * 1024)
+    OSC_CUDA(cudaFuncSetAttribute(knn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  dim3 grid((unsigned)((n_rows + TM - 1) / TM), (unsigned)batch);
+  knn_simt_kernel<<<grid, 256, smem, st>>>(Yq, Yall, n_rows, row0, N, D, kc, kcp, cand_idx,
+                                           cand_sim);
+  OSC_LAUNCH_CHECK("knn_simt_kernel");
+  return OSC_OK;
+}
+
+int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t N,
+                   int D, const int32_t* cand_idx, int kc, int k, int32_t* top_idx, float* top_sim,
+                   float* gap, cudaStream_t st) {
+  const int warps = 8;
+  const size_t smem = (size_t)warps * kc * (sizeof(float) + sizeof(int));
+  dim3 grid((unsigned)((n_rows + warps - 1) / warps), (unsigned)batch);
+  knn_rescore_kernel<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k,
+                                                     top_idx, top_sim, gap);
+  OSC_LAUNCH_CHECK("knn_rescore_kernel");
+  return OSC_OK;
+}
+
+}  // namespace osc

@@ -1,0 +1,590 @@
+// K2: multi-RHS Jacobi-PCG on the ELL graph (single lattice, vectors in HBM).
+//
+//   lattice.py:171-192 / :245-259  operator, right-hand side, Jacobi diagonal
+//   solver.py:15-37                per-column alpha/beta recurrences, max-column stop test
+//
+// Sparse operator, chi' = chain_present && lamP > 0:
+//   M x_i      = (lamG + lamC + chi' lamP + lamQ b_i) x_i - lamC sum_j W_ij x_j - chi' lamP sum_j Wp_ij x_j
+//   settle     : Aop = I + dt M ;  Mdiag_i = 1 + dt (lamG + lamQ b_i + chi lamP)
+//   stationary : Aop = M        ;  Mdiag_i =          lamG + lamQ b_i + chi lamP
+//
+// HBM-bound.  Thread layout: blockDim = (CX column groups of VEC floats, RY row lanes); a
+// block owns a contiguous row range, every thread keeps fp64 partial sums for its columns,
+// partials go to part[block][D] and a second tiny kernel reduces them in a fixed order
+// (run-to-run deterministic -- the stop test is a knife edge at large N).
+#include "common.cuh"
+
+namespace osc {
+
+struct Coef {
+  float lamG, lamC, lamQ, lamP_op, lamP_md, dt;
+  int settle, jacobi;
+};
+
+static Coef make_coef(const osc_params_t* p, int mode, float dt, int jacobi) {
+  Coef c;
+  c.lamG = p->lamG;
+  c.lamC = p->lamC;
+  c.lamQ = p->lamQ;
+  c.lamP_op = (p->chain_present && p->lamP > 0.f) ? p->lamP : 0.f;
+  c.lamP_md = p->chain_present ? p->lamP : 0.f;
+  c.dt = dt;
+  c.settle = (mode == OSC_MODE_SETTLE);
+  c.jacobi = jacobi;
+  return c;
+}
+
+__device__ __forceinline__ float op_diag(const Coef& c, float b) {
+  const float m = (c.lamG + c.lamC + c.lamP_op) + c.lamQ * b;
+  return c.settle ? 1.0f + c.dt * m : m;
+}
+__device__ __forceinline__ float op_offc(const Coef& c) { return c.settle ? c.dt * c.lamC : c.lamC; }
+__device__ __forceinline__ float op_offp(const Coef& c) {
+  return c.settle ? c.dt * c.lamP_op : c.lamP_op;
+}
+// lattice.py:187-192 / :257-259 (evaluated in the reference's order)
+__device__ __forceinline__ float md_diag(const Coef& c, float b) {
+  const float base = __fadd_rn(__fadd_rn(c.lamG, __fmul_rn(c.lamQ, b)), c.lamP_md);
+  return c.settle ? __fadd_rn(1.0f, __fmul_rn(c.dt, base)) : base;
+}
+__device__ __forceinline__ float precond(const Coef& c, float r, float md) {
+  return c.jacobi ? __fdiv_rn(r, md + 1e-12f) : r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void ldv(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = *p;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    *p = v[0];
+  }
+}
+
+struct Dims {
+  int64_t N, row0, n_local;
+  int D, n_blocks;
+};
+
+// reduce per-thread fp64 partials over the RY row lanes and store part[block][cols]
+template <int VEC>
+__device__ __forceinline__ void flush_partial(double (&acc)[VEC], double* sh, double* part, int D,
+                                              int cg, bool valid) {
+  const int CX = blockDim.x, RY = blockDim.y;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) sh[((size_t)threadIdx.y * CX + threadIdx.x) * VEC + v] = acc[v];
+  __syncthreads();
+  if (threadIdx.y == 0 && valid) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      double s = 0.0;
+      for (int y = 0; y < RY; ++y) s += sh[((size_t)y * CX + threadIdx.x) * VEC + v];
+      part[(size_t)blockIdx.x * D + cg * VEC + v] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- setup: x0 and right-hand side
+template <int VEC>
+__global__ void pcg_setup_kernel(Dims dm, Coef c, int warm, float w, const float* __restrict__ Y,
+                                 const float* __restrict__ U, const float* __restrict__ psi,
+                                 const float* __restrict__ gates, float* __restrict__ X,
+                                 float* __restrict__ Bv) {
+  const int CG = dm.D / VEC;
+  const int64_t total = dm.n_local * CG;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / CG;
+    const int cg = (int)(e - i * CG);
+    const int64_t o = i * dm.D + cg * VEC;
+    float y[VEC], u[VEC], q[VEC], x0[VEC], bv[VEC];
+    ldv<VEC>(Y + o, y);
+    ldv<VEC>(U + o, u);
+    ldv<VEC>(psi + cg * VEC, q);
+    const float b = gates ? gates[i] : 1.0f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float rhs = __fadd_rn(__fmul_rn(c.lamG, y[v]), __fmul_rn(c.lamQ, __fmul_rn(b, q[v])));
+      bv[v] = c.settle ? __fadd_rn(u[v], __fmul_rn(c.dt, rhs)) : rhs;
+      if (!c.settle || !warm) x0[v] = y[v];
+      else if (w <= 0.f) x0[v] = u[v];
+      else x0[v] = __fadd_rn(__fmul_rn(1.0f - w, y[v]), __fmul_rn(w, u[v]));
+    }
+    stv<VEC>(X + o, x0);
+    stv<VEC>(Bv + o, bv);
+  }
+}
+
+// ---------------------------------------------------------------- SpMM (+dot / +initial residual)
+struct GraphView {
+  const int32_t* nbr;
+  const float* W;
+  const int32_t* deg;
+  int k;
+};
+struct ChainView {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* Wp;
+  const int32_t* slot;  // nullptr => no chain
+};
+
+// RES0 = false: AP = Aop(V); part = sum_i V_i * AP_i
+// RES0 = true : R  = Bv - Aop(V) (in place over RBv); P = precond(R); part = sum_i R_i * Z_i
+template <int VEC, bool RES0>
+__global__ void __launch_bounds__(256)
+pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
+                const float* __restrict__ Vall, float* __restrict__ out, float* __restrict__ Pout,
+                double* __restrict__ part) {
+  extern __shared__ double sh[];
+  const int CG = dm.D / VEC;
+  const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
+  const int64_t r_beg = (int64_t)blockIdx.x * rpb;
+  const int64_t r_end = min(dm.n_local, r_beg + rpb);
+  const float offc = op_offc(c), offp = op_offp(c);
+  for (int cg = threadIdx.x; cg < (CG + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
+       cg += blockDim.x) {
+    double acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+    if (cg < CG) {
+      const int co = cg * VEC;
+      for (int64_t i = r_beg + threadIdx.y; i < r_end; i += blockDim.y) {
+        const int64_t gi = dm.row0 + i;
+        float own[VEC], s[VEC];
+        ldv<VEC>(Vall + gi * dm.D + co, own);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+        const int n = g.deg[i];
+        const int32_t* nb = g.nbr + i * g.k;
+        const float* wt = g.W + i * g.k;
+#pragma unroll 4
+        for (int t = 0; t < n; ++t) {
+          const int64_t j = nb[t];
+          const float w = wt[t];
+          float x[VEC];
+          ldv<VEC>(Vall + j * dm.D + co, x);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[v], s[v]);
+        }
+        const float b = gates ? gates[i] : 1.0f;
+        const float dg = op_diag(c, b);
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v] = dg * own[v] - offc * s[v];
+        if (ch.slot != nullptr && offp != 0.f) {
+          const int sl = ch.slot[gi];
+          if (sl >= 0) {
+            float sp[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sp[v] = 0.f;
+            for (int e = ch.rowptr[sl]; e < ch.rowptr[sl + 1]; ++e) {
+              float x[VEC];
+              ldv<VEC>(Vall + (int64_t)ch.col[e] * dm.D + co, x);
+              const float w = ch.Wp[e];
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) sp[v] = fmaf(w, x[v], sp[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) o[v] -= offp * sp[v];
+          }
+        }
+        if constexpr (RES0) {
+          float bv[VEC], r[VEC], z[VEC];
+          ldv<VEC>(out + i * dm.D + co, bv);
+          const float md = md_diag(c, b);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            r[v] = bv[v] - o[v];
+            z[v] = precond(c, r[v], md);
+            acc[v] += (double)r[v] * (double)z[v];
+          }
+          stv<VEC>(out + i * dm.D + co, r);
+          stv<VEC>(Pout + i * dm.D + co, z);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += (double)own[v] * (double)o[v];
+          stv<VEC>(out + i * dm.D + co, o);
+        }
+      }
+    }
+    flush_partial<VEC>(acc, sh, part, dm.D, cg, cg < CG);
+  }
+}
+
+// ---------------------------------------------------------------- x, r update + partial rr, rz'
+template <int VEC>
+__global__ void __launch_bounds__(256)
+pcg_update_kernel(Dims dm, Coef c, const float* __restrict__ gates, const float* __restrict__ rz,
+                  const float* __restrict__ pap, const float* __restrict__ P,
+                  const float* __restrict__ AP, float* __restrict__ X, float* __restrict__ R,
+                  double* __restrict__ part_rr, double* __restrict__ part_rz) {
+  extern __shared__ double sh[];
+  const int CG = dm.D / VEC;
+  const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
+  const int64_t r_beg = (int64_t)blockIdx.x * rpb;
+  const int64_t r_end = min(dm.n_local, r_beg + rpb);
+  for (int cg = threadIdx.x; cg < (CG + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
+       cg += blockDim.x) {
+    double arr[VEC], arz[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) arr[v] = arz[v] = 0.0;
+    if (cg < CG) {
+      const int co = cg * VEC;
+      float alpha[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) alpha[v] = __fdiv_rn(rz[co + v], pap[co + v] + 1e-18f);
+      for (int64_t i = r_beg + threadIdx.y; i < r_end; i += blockDim.y) {
+        const int64_t o = i * dm.D + co;
+        float p[VEC], ap[VEC], x[VEC], r[VEC];
+        ldv<VEC>(P + o, p);
+        ldv<VEC>(AP + o, ap);
+        ldv<VEC>(X + o, x);
+        ldv<VEC>(R + o, r);
+        const float md = md_diag(c, gates ? gates[i] : 1.0f);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          x[v] = __fadd_rn(x[v], __fmul_rn(p[v], alpha[v]));
+          r[v] = __fsub_rn(r[v], __fmul_rn(ap[v], alpha[v]));
+          const float z = precond(c, r[v], md);
+          arr[v] += (double)r[v] * (double)r[v];
+          arz[v] += (double)r[v] * (double)z;
+        }
+        stv<VEC>(X + o, x);
+        stv<VEC>(R + o, r);
+      }
+    }
+    flush_partial<VEC>(arr, sh, part_rr, dm.D, cg, cg < CG);
+    flush_partial<VEC>(arz, sh, part_rz, dm.D, cg, cg < CG);
+  }
+}
+
+// ---------------------------------------------------------------- p = z + beta p
+template <int VEC>
+__global__ void pcg_pupdate_kernel(Dims dm, Coef c, const float* __restrict__ gates,
+                                   const float* __restrict__ rz_new,
+                                   const float* __restrict__ rz_old, const float* __restrict__ R,
+                                   float* __restrict__ P) {
+  const int CG = dm.D / VEC;
+  const int64_t total = dm.n_local * CG;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / CG;
+    const int cg = (int)(e - i * CG);
+    const int co = cg * VEC;
+    const int64_t o = i * dm.D + co;
+    float r[VEC], p[VEC];
+    ldv<VEC>(R + o, r);
+    ldv<VEC>(P + o, p);
+    const float md = md_diag(c, gates ? gates[i] : 1.0f);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float beta = __fdiv_rn(rz_new[co + v], rz_old[co + v] + 1e-18f);
+      p[v] = __fadd_rn(precond(c, r[v], md), __fmul_rn(p[v], beta));
+    }
+    stv<VEC>(P + o, p);
+  }
+}
+
+// diff = U - Ustar (receipts.py:21)
+__global__ void diff_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                            float* __restrict__ out, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = __fsub_rn(a[e], b[e]);
+}
+
+// ---------------------------------------------------------------- column reduction of partials
+__global__ void __launch_bounds__(1024)
+pcg_reduce_kernel(const double* __restrict__ part, int n_blocks, int D, float* __restrict__ out,
+                  float* __restrict__ d_max, double* __restrict__ d_total) {
+  __shared__ float smax[32];
+  __shared__ double ssum[32];
+  float mx = 0.f;
+  double tot = 0.0;
+  for (int cidx = threadIdx.x; cidx < D; cidx += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += part[(size_t)b * D + cidx];
+    const float f = (float)s;
+    out[cidx] = f;
+    mx = fmaxf(mx, __fsqrt_rn(fmaxf(f, 0.f)));
+    tot += s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) {
+    smax[threadIdx.x >> 5] = mx;
+    ssum[threadIdx.x >> 5] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    double t = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) {
+      m = fmaxf(m, smax[w]);
+      t += ssum[w];
+    }
+    if (d_max != nullptr) *d_max = m;
+    if (d_total != nullptr) *d_total = t;
+  }
+}
+
+// ================================================================= host side
+static void block_shape(int D, int& vec, dim3& blk) {
+  vec = (D % 4 == 0) ? 4 : 1;
+  const int CG = D / vec;
+  const int cx = CG < 256 ? CG : 256;
+  int ry = 256 / cx;
+  if (ry < 1) ry = 1;
+  blk = dim3(cx, ry, 1);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static Dims to_dims(const osc_pcg_dims_t* d) {
+  Dims r;
+  r.N = d->N;
+  r.row0 = d->row0;
+  r.n_local = d->n_local;
+  r.D = d->D;
+  r.n_blocks = d->n_blocks;
+  return r;
+}
+
+static GraphView gview(const osc_graph_t* g) { return GraphView{g->nbr, g->W, g->deg, g->k}; }
+static ChainView cview(const osc_chain_t* c) {
+  if (c == nullptr || c->n_rows == 0) return ChainView{nullptr, nullptr, nullptr, nullptr};
+  return ChainView{c->rowptr, c->col, c->Wp, c->slot};
+}
+
+static int ew_grid(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int pcg_plan(osc_pcg_dims_t* d, size_t* ws) {
+  OSC_REQUIRE(d != nullptr, "dims is NULL");
+  OSC_REQUIRE(d->D >= 1 && d->N >= 0 && d->n_local >= 0 && d->row0 >= 0, "bad dims");
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  int64_t nb = (d->n_local + blk.y - 1) / blk.y;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  d->n_blocks = (int)nb;
+  if (ws != nullptr) {
+    const size_t vecb = align_up((size_t)d->n_local * d->D * sizeof(float));
+    const size_t partb = align_up((size_t)nb * d->D * sizeof(double));
+    const size_t colb = align_up((size_t)d->D * sizeof(float));
+    *ws = 3 * vecb + 3 * partb + 5 * colb + 1024;
+  }
+  return OSC_OK;
+}
+
+#define OSC_VEC_DISPATCH(vec, ...)   \
+  if ((vec) == 4) {                  \
+    constexpr int VEC = 4;           \
+    __VA_ARGS__                      \
+  } else {                           \
+    constexpr int VEC = 1;           \
+    __VA_ARGS__                      \
+  }
+
+int pcg_setup(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int warm,
+              float inertia, const float* Y, const float* U, const float* psi, const float* gates,
+              float* X, float* Bv, cudaStream_t st) {
+  if (d->n_local == 0) return OSC_OK;
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  if (!(aligned16(Y) && aligned16(U) && aligned16(psi) && aligned16(X) && aligned16(Bv))) vec = 1;
+  Coef c = make_coef(prm, mode, dt, 1);
+  float w = inertia < 0.f ? 0.f : (inertia > 1.f ? 1.f : inertia);
+  const int64_t total = d->n_local * (d->D / vec);
+  OSC_VEC_DISPATCH(vec, pcg_setup_kernel<VEC><<<ew_grid(total), 256, 0, st>>>(
+                            to_dims(d), c, warm, w, Y, U, psi, gates, X, Bv);)
+  OSC_LAUNCH_CHECK("pcg_setup_kernel");
+  return OSC_OK;
+}
+
+static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
+                       const osc_chain_t* chain, const osc_params_t* prm, int mode, float dt,
+                       int jacobi, const float* gates, const float* Vall, float* out, float* Pout,
+                       double* part, cudaStream_t st) {
+  if (d->n_local == 0) return OSC_OK;
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  if (!(aligned16(Vall) && aligned16(out) && (Pout == nullptr || aligned16(Pout)))) {
+    if (vec == 4) return fail(OSC_ERR_INVALID, "pcg: vectors must be 16-byte aligned when D % 4 == 0");
+  }
+  Coef c = make_coef(prm, mode, dt, jacobi);
+  const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double);
+  if (res0) {
+    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, true><<<d->n_blocks, blk, smem, st>>>(
+                              to_dims(d), c, gview(g), cview(chain), gates, Vall, out, Pout, part);)
+  } else {
+    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, false><<<d->n_blocks, blk, smem, st>>>(
+                              to_dims(d), c, gview(g), cview(chain), gates, Vall, out, Pout, part);)
+  }
+  OSC_LAUNCH_CHECK("pcg_spmm_kernel");
+  return OSC_OK;
+}
+
+int pcg_residual0(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
+                  const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates,
+                  const float* Xall, float* RBv, float* P, double* part_rz, cudaStream_t st) {
+  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, Xall, RBv, P, part_rz, st);
+}
+
+int pcg_spmm_dot(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
+                 const osc_params_t* prm, int mode, float dt, const float* gates, const float* Pall,
+                 float* AP, double* part_pap, cudaStream_t st) {
+  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, Pall, AP, nullptr, part_pap, st);
+}
+
+int pcg_reduce(const double* part, int n_blocks, int D, float* out, float* d_max, double* d_total,
+               cudaStream_t st) {
+  const int threads = D < 1024 ? ((D + 31) / 32 * 32) : 1024;
+  pcg_reduce_kernel<<<1, threads, 0, st>>>(part, n_blocks, D, out, d_max, d_total);
+  OSC_LAUNCH_CHECK("pcg_reduce_kernel");
+  return OSC_OK;
+}
+
+int pcg_update(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int jacobi,
+               const float* gates, const float* rz, const float* pap, const float* P,
+               const float* AP, float* X, float* R, double* part_rr, double* part_rz,
+               cudaStream_t st) {
+  if (d->n_local == 0) return OSC_OK;
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  Coef c = make_coef(prm, mode, dt, jacobi);
+  const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double);
+  OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC><<<d->n_blocks, blk, smem, st>>>(
+                            to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz);)
+  OSC_LAUNCH_CHECK("pcg_update_kernel");
+  return OSC_OK;
+}
+
+int pcg_pupdate(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int jacobi,
+                const float* gates, const float* rz_new, const float* rz_old, const float* R,
+                float* P, cudaStream_t st) {
+  if (d->n_local == 0) return OSC_OK;
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  Coef c = make_coef(prm, mode, dt, jacobi);
+  const int64_t total = d->n_local * (d->D / vec);
+  OSC_VEC_DISPATCH(vec, pcg_pupdate_kernel<VEC><<<ew_grid(total), 256, 0, st>>>(
+                            to_dims(d), c, gates, rz_new, rz_old, R, P);)
+  OSC_LAUNCH_CHECK("pcg_pupdate_kernel");
+  return OSC_OK;
+}
+
+int pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, int mode,
+              float dt, int warm, float inertia, int jacobi, double tol, int max_iters,
+              const float* Y, const float* U, const float* psi, const float* gates, int D, float* X,
+              int* h_iters, float* h_res, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  OSC_REQUIRE(g != nullptr && prm != nullptr && Y != nullptr && X != nullptr && psi != nullptr,
+              "pcg_solve: NULL argument");
+  OSC_REQUIRE(g->batch == 1, "pcg_solve handles one lattice (use osc_batched_settle)");
+  if (U == nullptr) U = Y;
+  osc_pcg_dims_t d{g->N, 0, g->N, D, 0};
+  size_t need = 0;
+  int rc = pcg_plan(&d, &need);
+  if (rc) return rc;
+  if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
+  Arena ar(workspace, ws_bytes);
+  const size_t nd = (size_t)g->N * D;
+  float* R = ar.take<float>(nd);
+  float* P = ar.take<float>(nd);
+  float* AP = ar.take<float>(nd);
+  double* part_a = ar.take<double>((size_t)d.n_blocks * D);
+  double* part_b = ar.take<double>((size_t)d.n_blocks * D);
+  double* part_c = ar.take<double>((size_t)d.n_blocks * D);
+  float* rz = ar.take<float>(D);
+  float* rz_new = ar.take<float>(D);
+  float* pap = ar.take<float>(D);
+  float* rr = ar.take<float>(D);
+  float* d_res = ar.take<float>(64);
+  if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
+  (void)part_c;
+  int it = 0;
+  float res = __builtin_nanf("");
+  if (g->N > 0 && max_iters >= 1) {
+    if ((rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, R, st))) return rc;
+    if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) return rc;
+    if ((rc = pcg_reduce(part_a, d.n_blocks, D, rz, nullptr, nullptr, st))) return rc;
+    for (it = 1; it <= max_iters; ++it) {
+      if ((rc = pcg_spmm_dot(&d, g, chain, prm, mode, dt, gates, P, AP, part_a, st))) return rc;
+      if ((rc = pcg_reduce(part_a, d.n_blocks, D, pap, nullptr, nullptr, st))) return rc;
+      if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, X, R, part_a, part_b, st)))
+        return rc;
+      if ((rc = pcg_reduce(part_a, d.n_blocks, D, rr, d_res, nullptr, st))) return rc;
+      if ((rc = pcg_reduce(part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st))) return rc;
+      OSC_CUDA(cudaMemcpyAsync(&res, d_res, sizeof(float), cudaMemcpyDeviceToHost, st));
+      OSC_CUDA(cudaStreamSynchronize(st));
+      if ((double)res <= tol) break;  // solver.py:29-31
+      if (it == max_iters) break;
+      if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st))) return rc;
+      float* t = rz;
+      rz = rz_new;
+      rz_new = t;
+    }
+    if (it > max_iters) it = max_iters;
+  } else if (g->N == 0) {
+    it = 0;
+  }
+  if (h_iters) *h_iters = it;
+  if (h_res) *h_res = res;
+  return OSC_OK;
+}
+
+// deltaH = sum_c diff_c . (M diff)_c   (receipts.py:21-25)
+int delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, const float* U,
+            const float* Ustar, const float* gates, int D, double* h_out, void* workspace,
+            size_t ws_bytes, cudaStream_t st) {
+  OSC_REQUIRE(g != nullptr && prm != nullptr && U != nullptr && Ustar != nullptr && h_out != nullptr,
+              "delta_h: NULL argument");
+  OSC_REQUIRE(g->batch == 1, "delta_h handles one lattice");
+  osc_pcg_dims_t d{g->N, 0, g->N, D, 0};
+  size_t need = 0;
+  int rc = pcg_plan(&d, &need);
+  if (rc) return rc;
+  if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "delta_h: workspace too small");
+  *h_out = 0.0;
+  if (g->N == 0) return OSC_OK;
+  Arena ar(workspace, ws_bytes);
+  const size_t nd = (size_t)g->N * D;
+  float* diff = ar.take<float>(nd);
+  float* Md = ar.take<float>(nd);
+  double* part = ar.take<double>((size_t)d.n_blocks * D);
+  float* colsum = ar.take<float>(D);
+  double* total = ar.take<double>(8);
+  if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "delta_h: workspace too small");
+  diff_kernel<<<ew_grid((int64_t)nd), 256, 0, st>>>(U, Ustar, diff, (int64_t)nd);
+  OSC_LAUNCH_CHECK("diff_kernel");
+  if ((rc = pcg_spmm_dot(&d, g, chain, prm, OSC_MODE_STATIONARY, 0.f, gates, diff, Md, part, st)))
+    return rc;
+  if ((rc = pcg_reduce(part, d.n_blocks, D, colsum, nullptr, total, st))) return rc;
+  OSC_CUDA(cudaMemcpyAsync(h_out, total, sizeof(double), cudaMemcpyDeviceToHost, st));
+  OSC_CUDA(cudaStreamSynchronize(st));
+  return OSC_OK;
+}
+
+}  // namespace osc

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # gpu tests are selected with -m gpu; when selected without a device, fail loudly
+    # instead of silently skipping (a silent skip would hide a missing CUDA path).
+    pass
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
