@@ -90,7 +90,8 @@ class BatchedLattices:
             return
         kc = min(k + 4, N - 1)
         rows = B * N
-        use_tc = self._engine != _cabi.KNN_SIMT and bool(lib.osc_knn_tc_supported(N, D, kc))
+        use_tc = (self._engine != _cabi.KNN_SIMT and bool(lib.osc_knn_tc_supported(N, D, kc))
+                  and (self._engine == _cabi.KNN_TC or N >= 256))
         if self._engine == _cabi.KNN_TC and not use_tc:
             raise _cabi.OscillinkNativeError("tensor-core kNN engine does not cover this shape")
         self.engine_used = "tc" if use_tc else "simt"

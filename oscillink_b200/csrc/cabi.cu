@@ -84,8 +84,10 @@ static int candidate_width(int64_t N, int k) {
 static int pick_engine(int flags, int64_t N, int D, int kc) {
   const int want = flags & 3;
   if (want == OSC_KNN_SIMT) return OSC_KNN_SIMT;
-  if (knn_tc_supported(N, D, kc)) return OSC_KNN_TC;
-  return (want == OSC_KNN_TC) ? -1 : OSC_KNN_SIMT;
+  const int ok = knn_tc_supported(N, D, kc);
+  if (want == OSC_KNN_TC) return ok ? OSC_KNN_TC : -1;
+  // AUTO: 128x256 tensor tiles only pay off once a lattice fills a few of them
+  return (ok && N >= 256) ? OSC_KNN_TC : OSC_KNN_SIMT;
 }
 
 }  // namespace osc

@@ -1,9 +1,394 @@
-// K1 tensor-core engine (tcgen05 3xTF32) -- placeholder until the kernel lands.
+// K1 tensor-core engine: TMA-staged 3xTF32 similarity GEMM on tcgen05 with the top-k fused into
+// the TMEM epilogue -- the N x N similarity matrix never reaches HBM (graph.py:36-37,59).
+//
+//   S_tile = Ahi*Bhi^T + Ahi*Blo^T + Alo*Bhi^T      (fp32 accumulate in TMEM; hi = tf32(x),
+//                                                     lo = tf32(x - hi): ~2^-22 relative)
+//
+// One CTA per SM (persistent).  A work item is (lattice b, 128-row panel); the CTA sweeps all
+// 256-column tiles of that lattice, double-buffering the 128x256 fp32 accumulator in TMEM
+// (2 x 256 = all 512 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.3d, SWIZZLE_128B, 32-float K blocks;
+//                                 hi and lo of A and B ride in the SAME stage so one stage
+//                                 feeds all three products -> 96 KB / 3 MMA groups)
+//   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8) + TMEM alloc
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b.x32: thread == TMEM lane == similarity row;
+//                                 per-row sorted top-KC list held in registers, one compare
+//                                 against the running threshold rejects almost every column)
+//
+// The candidate lists (approximate scores) feed knn_rescore_kernel, which fixes the final
+// neighbour sets in the canonical order -- both engines therefore yield identical graphs.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "common.cuh"
+
 namespace osc {
-int knn_tc_supported(int64_t, int, int) { return 0; }
-int launch_knn_tc(const float*, const float*, const float*, const float*, int64_t, int64_t, int64_t,
-                  int64_t, int, int, int32_t*, float*, cudaStream_t) {
-  return fail(OSC_ERR_UNSUPPORTED, "tensor-core kNN engine not built");
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 32;  // floats: 128 B = one SWIZZLE_128B row
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // Ahi, Alo, Bhi, Blo
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcParams {
+  int64_t batch, n_rows, row0, N;
+  int D, kc;
+  int panels, col_tiles, k_blocks;
+  int64_t total_work;
+  int32_t* cand_idx;
+  float* cand_sim;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Pipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+// ---------------------------------------------------------------- kernel
+template <int KC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+              const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+              TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull0 = bars + 16 * TC_STAGES,
+                 tempty0 = tfull0 + 16;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      Pipe p;
+      for (int64_t w = blockIdx.x; w < P.total_work; w += gridDim.x) {
+        const int b = (int)(w / P.panels);
+        const int m0 = (int)(w % P.panels) * TC_BM;
+        for (int ct = 0; ct < P.col_tiles; ++ct) {
+          const int n0 = ct * TC_BN;
+          for (int kb = 0; kb < P.k_blocks; ++kb) {
+            mbar_wait(empty0 + 8 * p.stage, p.phase ^ 1u);
+            const uint32_t sb = base + p.stage * TC_STAGE_BYTES;
+            const uint32_t fb = full0 + 8 * p.stage;
+            mbar_expect_tx(fb, TC_STAGE_BYTES);
+            tma_load_3d(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
+            tma_load_3d(&tm_q_lo, sb + TC_A_BYTES, fb, kb * TC_BK, m0, b);
+            tma_load_3d(&tm_a_hi, sb + 2 * TC_A_BYTES, fb, kb * TC_BK, n0, b);
+            tma_load_3d(&tm_a_lo, sb + 2 * TC_A_BYTES + TC_B_BYTES, fb, kb * TC_BK, n0, b);
+            p.advance(TC_STAGES);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                           ((uint32_t)(TC_BM >> 4) << 24);
+    Pipe p, acc;
+    for (int64_t w = blockIdx.x; w < P.total_work; w += gridDim.x) {
+      for (int ct = 0; ct < P.col_tiles; ++ct) {
+        mbar_wait(tempty0 + 8 * acc.stage, acc.phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc.stage * TC_BN);
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(full0 + 8 * p.stage, p.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sb = base + p.stage * TC_STAGE_BYTES;
+            const uint64_t ah = umma_desc(sb), al = umma_desc(sb + TC_A_BYTES),
+                           bh = umma_desc(sb + 2 * TC_A_BYTES),
+                           bl = umma_desc(sb + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const uint64_t o = (uint64_t)((ks * 32) >> 4);  // +32 B per K=8 step inside the swizzle row
+              tc_mma_tf32(tacc, al + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
+              tc_mma_tf32(tacc, ah + o, bl + o, idesc, 1u);
+              tc_mma_tf32(tacc, ah + o, bh + o, idesc, 1u);
+            }
+            tc_commit(empty0 + 8 * p.stage);  // smem stage free once these MMAs retire
+            if (kb == P.k_blocks - 1) tc_commit(tfull0 + 8 * acc.stage);
+          }
+          __syncwarp();
+          p.advance(TC_STAGES);
+        }
+        acc.advance(2);
+      }
+    }
+  } else {
+    // ===================== epilogue: fused per-row top-KC
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int r_tile = quarter * 32 + lane;
+    Pipe acc;
+    for (int64_t w = blockIdx.x; w < P.total_work; w += gridDim.x) {
+      const int64_t b = w / P.panels;
+      const int m0 = (int)(w % P.panels) * TC_BM;
+      const int gi = m0 + r_tile;                 // query row inside the panel set
+      const int self = (int)(P.row0 + gi);        // its column id
+      const bool row_ok = gi < P.n_rows;
+      float val[KC];
+      int idx[KC];
+#pragma unroll
+      for (int i = 0; i < KC; ++i) {
+        val[i] = -INFINITY;
+        idx[i] = -1;
+      }
+      for (int ct = 0; ct < P.col_tiles; ++ct) {
+        const int n0 = ct * TC_BN;
+        mbar_wait(tfull0 + 8 * acc.stage, acc.phase);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc.stage * TC_BN);
+#pragma unroll 1
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          const int c0 = n0 + ch * 32;
+          if (c0 >= P.N) break;  // warp-uniform
+          float v[32];
+          tmem_ld32(trow + (uint32_t)(ch * 32), v);
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = c0 + i;
+              const float s = (col < P.N && col != self) ? v[i] : -INFINITY;
+              if (s > val[KC - 1]) {
+                // sorted insert (descending); strict '>' keeps the smaller column on ties
+#pragma unroll
+                for (int p = KC - 1; p > 0; --p) {
+                  const bool up = s > val[p - 1];
+                  const bool here = !up && (s > val[p]);
+                  const float nv = up ? val[p - 1] : (here ? s : val[p]);
+                  const int ni = up ? idx[p - 1] : (here ? col : idx[p]);
+                  val[p] = nv;
+                  idx[p] = ni;
+                }
+                if (s > val[0]) {
+                  val[0] = s;
+                  idx[0] = col;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * acc.stage);
+        acc.advance(2);
+      }
+      if (row_ok) {
+        const int64_t o = (b * P.n_rows + gi) * P.kc;
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+          if (i < P.kc) {
+            P.cand_idx[o + i] = idx[i];
+            P.cand_sim[o + i] = val[i];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ================================================================= host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [batch][rows][D] fp32, box = {32 floats, box_rows, 1}, SWIZZLE_128B, OOB -> 0
+static int make_map(CUtensorMap* m, const float* ptr, int64_t batch, int64_t rows, int D, int box_rows) {
+  EncodeTiledFn enc = encoder();
+  if (enc == nullptr) return fail(OSC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)rows * D * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OSC_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return OSC_OK;
+}
+
+int knn_tc_supported(int64_t N, int D, int kc) {
+  if (N < 2 || N > 0x7fffffffLL || D < 4 || D % 4 != 0 || kc < 1 || kc > 32) return 0;
+  int dev = 0, mj = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return mj == 10 ? 1 : 0;
+}
+
+int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
+                  int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
+                  int32_t* cand_idx, float* cand_sim, cudaStream_t st) {
+  if (!knn_tc_supported(N, D, kc)) return fail(OSC_ERR_UNSUPPORTED, "knn_tc: shape not covered");
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  OSC_REQUIRE(a16(q_hi) && a16(q_lo) && a16(all_hi) && a16(all_lo), "knn_tc: operands must be 16 B aligned");
+  CUtensorMap mqh, mql, mah, mal;
+  int rc;
+  if ((rc = make_map(&mqh, q_hi, batch, n_rows, D, TC_BM))) return rc;
+  if ((rc = make_map(&mql, q_lo, batch, n_rows, D, TC_BM))) return rc;
+  if ((rc = make_map(&mah, all_hi, batch, N, D, TC_BN))) return rc;
+  if ((rc = make_map(&mal, all_lo, batch, N, D, TC_BN))) return rc;
+  TcParams P;
+  P.batch = batch;
+  P.n_rows = n_rows;
+  P.row0 = row0;
+  P.N = N;
+  P.D = D;
+  P.kc = kc;
+  P.panels = (int)((n_rows + TC_BM - 1) / TC_BM);
+  P.col_tiles = (int)((N + TC_BN - 1) / TC_BN);
+  P.k_blocks = (D + TC_BK - 1) / TC_BK;
+  P.total_work = batch * P.panels;
+  P.cand_idx = cand_idx;
+  P.cand_sim = cand_sim;
+  const int64_t sms = sm_count();
+  const unsigned grid = (unsigned)(P.total_work < sms ? P.total_work : sms);
+  if (kc <= 16) {
+    OSC_CUDA(cudaFuncSetAttribute(knn_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    knn_tc_kernel<16><<<grid, TC_THREADS, TC_SMEM, st>>>(mqh, mql, mah, mal, P);
+  } else {
+    OSC_CUDA(cudaFuncSetAttribute(knn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    knn_tc_kernel<32><<<grid, TC_THREADS, TC_SMEM, st>>>(mqh, mql, mah, mal, P);
+  }
+  OSC_LAUNCH_CHECK("knn_tc_kernel");
+  return OSC_OK;
+}
+
 }  // namespace osc

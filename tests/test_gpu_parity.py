@@ -252,3 +252,42 @@ def test_null_cap_env(api, monkeypatch):
     assert s["null_cap_applied"] and s["total_null_points"] == 80 and s["returned_null_points"] == 5
     zs = [e["z"] for e in rec["null_points"]]
     assert zs == sorted(zs, reverse=True)
+
+
+@pytest.mark.parametrize("shape", [(1, 300, 64, 6), (2, 1200, 384, 8), (1, 97, 20, 5), (3, 640, 128, 8),
+                                   (1, 3000, 768, 16), (1, 130, 4, 28)])
+def test_tc_and_simt_engines_build_identical_graphs(shape):
+    """tcgen05 3xTF32 engine vs CUDA-core engine: candidate order may differ inside near-ties,
+    the canonical rescoring must make the final top-k tables and weights bit-identical."""
+    import ctypes as C
+
+    import torch
+
+    from oscillink_b200 import _cabi
+
+    B, N, D, k = shape
+    lib = _cabi.load()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(N + D)
+    Y = torch.randn((B, N, D), generator=gen, device=dev)
+    res = {}
+    for name, eng in (("simt", _cabi.KNN_SIMT), ("tc", _cabi.KNN_TC)):
+        nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+        A = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+        W = torch.empty_like(A)
+        deg = torch.empty((B, N), dtype=torch.int32, device=dev)
+        sd = torch.empty((B, N), dtype=torch.float32, device=dev)
+        nnz = torch.zeros(B, dtype=torch.int64, device=dev)
+        gap = torch.empty((B, N), dtype=torch.float32, device=dev)
+        need = C.c_size_t(0)
+        _cabi.check(lib.osc_knn_build_workspace(B, N, D, k, eng, C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.osc_knn_build(Y.data_ptr(), B, N, D, k, 1.0, eng, nbr.data_ptr(), A.data_ptr(),
+                                      W.data_ptr(), deg.data_ptr(), sd.data_ptr(), nnz.data_ptr(),
+                                      gap.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream().cuda_stream), name)
+        torch.cuda.synchronize()
+        res[name] = (nbr.cpu().numpy(), A.cpu().numpy(), W.cpu().numpy(), nnz.cpu().numpy())
+    for a, b in zip(res["simt"], res["tc"]):
+        assert np.array_equal(a, b)
