@@ -206,11 +206,24 @@ int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params
                 double* h_deltaH, void* workspace, size_t ws_bytes, void* stream);
 
 /* Per-node terms (receipts.py:40-59) and null points (receipts.py:70-82), one pass.
- * coh/anchor/query: [N]; null_j[N] (-1 = none), null_z[N], null_R[N]. */
+ * coh/anchor/query: [N]; null_j[N] (-1 = none), null_z[N], null_R[N];
+ * row_mu/row_sigma (optional): the per-row mean / std+1e-12 of R over all N columns. */
 int osc_receipt_full(const osc_graph_t* g, const osc_params_t* prm, const float* Y,
                      const float* Ustar, const float* psi, const float* gates, int32_t D, float z_th,
                      float* coh, float* anchor, float* query, int32_t* null_j, float* null_z,
-                     float* null_R, void* stream);
+                     float* null_R, float* row_mu, float* row_sigma, void* stream);
+
+/* ------------------------------------------------------------------ f1/f2: bundle, chain receipt
+ * align_i = <U*_i/(||U*_i||+1e-12), psi/(||psi||+1e-12)>   (lattice.py:559-561) */
+int osc_row_align(const float* Ustar, const float* psi, int64_t N, int32_t D, float* align, void* stream);
+/* d2[p] = || V_i/(sd_i+1e-12) - V_j/(sd_j+1e-12) ||^2 for pairs[p] = (i,j)   (lattice.py:468-471) */
+int osc_pair_d2(const float* V, const float* sqrt_deg, const int32_t* pairs, int64_t M, int32_t D,
+                float* out, void* stream);
+/* greedy MMR over cosine-normalised anchors Yn (graph.py:114-133, lambda_div = 0.5):
+ * chosen[s] = argmax_i 0.5*score_i - 0.5*max_{j chosen} <Yn_i,Yn_j>, lowest index on ties */
+int osc_mmr_workspace(int64_t N, size_t* h_bytes);
+int osc_mmr_select(const float* Yn, const float* score, int64_t N, int32_t D, int32_t k, int32_t* chosen,
+                   void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ K3: batched serving
  * One persistent kernel settles `batch` independent lattices of equal (N, D, k):

@@ -87,7 +87,12 @@ PROTOTYPES = {
                               P(c_f64), c_void_p, c_size_t, c_void_p]),
     "osc_receipt_full": (C.c_int, [P(Graph), P(Params), c_void_p, c_void_p, c_void_p, c_void_p, c_i32,
                                    c_f32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p, c_void_p]),
+    "osc_row_align": (C.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_void_p]),
+    "osc_pair_d2": (C.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_void_p]),
+    "osc_mmr_workspace": (C.c_int, [c_i64, P(c_size_t)]),
+    "osc_mmr_select": (C.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
     "osc_batched_supported": (C.c_int, [c_i64, c_i32, c_i32]),
     "osc_batched_workspace": (C.c_int, [c_i64, c_i64, c_i32, P(c_size_t)]),
     "osc_batched_settle": (C.c_int, [P(Graph), P(Params), P(BatchedArgs), c_void_p, c_size_t, c_void_p]),

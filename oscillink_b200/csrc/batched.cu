@@ -17,9 +17,11 @@
 
 namespace osc {
 
-constexpr int BC = 8;     // columns per slab
-constexpr int BT = 640;   // threads per CTA
-constexpr int BW = BT / 32;
+constexpr int BC = 8;        // columns per slab
+constexpr int BT_MAX = 1024;  // threads per CTA are chosen per shape (multiple of 32)
+constexpr int BW_MAX = BT_MAX / 32;
+#define BT ((int)blockDim.x)
+#define BW ((int)(blockDim.x >> 5))
 
 struct BatchedK {
   const int32_t* nbr;
@@ -77,8 +79,9 @@ __device__ __forceinline__ float4 block_colsum(float4 v, float4* red, int lane, 
   if (lane < 2) red[warp * 2 + lane] = v;
   __syncthreads();
   float4 t = f4_zero();
+  const int nw = BW;
 #pragma unroll 4
-  for (int w = 0; w < BW; ++w) t = f4_add(t, red[w * 2 + half]);
+  for (int w = 0; w < nw; ++w) t = f4_add(t, red[w * 2 + half]);
   return t;
 }
 
@@ -88,10 +91,13 @@ struct Slab {
 };
 
 // A(p) for one task: diag*p_own - offc * sum_t W_t p[nbr_t]
+template <int KQ>
 __device__ __forceinline__ float4 apply_task(const float4* p_s, const ushort4* nbr_s,
-                                             const float4* w_s, int row, int half, int kq,
+                                             const float4* w_s, int row, int half, int kq_rt,
                                              float diag, float offc) {
   float4 acc = f4_zero();
+  const int kq = KQ > 0 ? KQ : kq_rt;
+#pragma unroll
   for (int c = 0; c < kq; ++c) {
     const ushort4 jj = nbr_s[row * kq + c];
     const float4 ww = w_s[row * kq + c];
@@ -107,7 +113,7 @@ __device__ __forceinline__ float4 apply_task(const float4* p_s, const ushort4* n
 
 // One PCG solve for this CTA's slab.  On exit st.X holds the solution.  Returns iterations;
 // *res_out the last max-column residual (group-wide).
-template <int TPT>
+template <int TPT, int KQ>
 __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max_iters, float4* p_s,
                           const float* gates_s, const ushort4* nbr_s, const float4* w_s,
                           float4* red, unsigned* sync_base, int G, const bool (&act)[TPT],
@@ -127,7 +133,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     if (act[m]) {
       const int q = tid + BT * m, row = q >> 1;
       const float b = gates_s[row];
-      const float4 a = apply_task(p_s, nbr_s, w_s, row, half, c.kq, c.diag0 + c.diag1 * b,
+      const float4 a = apply_task<KQ>(p_s, nbr_s, w_s, row, half, c.kq, c.diag0 + c.diag1 * b,
                                   c.offc);
       const float md = md_of(c, b) + 1e-12f;
       float4 r = st.R[m];
@@ -147,8 +153,8 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   int it = 0;
   float res = __int_as_float(0x7fc00000);
   for (it = 1; it <= max_iters; ++it) {
-    float4* redA = red + 1 * (BW * 2);
-    float4* redB = red + 2 * (BW * 2);  // two consecutive buffers (rr, rz')
+    float4* redA = red + 1 * (BW_MAX * 2);
+    float4* redB = red + 2 * (BW_MAX * 2);  // two consecutive buffers (rr, rz')
     // ---- Ap, p.Ap
     part = f4_zero();
 #pragma unroll
@@ -156,7 +162,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
       if (act[m]) {
         const int q = tid + BT * m, row = q >> 1;
         const float b = gates_s[row];
-        st.AP[m] = apply_task(p_s, nbr_s, w_s, row, half, c.kq, c.diag0 + c.diag1 * b,
+        st.AP[m] = apply_task<KQ>(p_s, nbr_s, w_s, row, half, c.kq, c.diag0 + c.diag1 * b,
                               c.offc);
         part = f4_add(part, f4_mul(p_s[q], st.AP[m]));
       }
@@ -203,14 +209,15 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     }
     if (lane < 2) {
       redB[warp * 2 + lane] = prr;
-      redB[BW * 2 + warp * 2 + lane] = prz;
+      redB[BW_MAX * 2 + warp * 2 + lane] = prz;
     }
     __syncthreads();
     float4 rr = f4_zero(), rzn = f4_zero();
+    const int nw = BW;
 #pragma unroll 4
-    for (int w = 0; w < BW; ++w) {
+    for (int w = 0; w < nw; ++w) {
       rr = f4_add(rr, redB[w * 2 + half]);
-      rzn = f4_add(rzn, redB[BW * 2 + w * 2 + half]);
+      rzn = f4_add(rzn, redB[BW_MAX * 2 + w * 2 + half]);
     }
     // slab max of the column residuals -> group-wide max (solver.py:29)
     float mx = fmaxf(fmaxf(rr.x, rr.y), fmaxf(rr.z, rr.w));
@@ -251,14 +258,15 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   return it;
 }
 
-template <int TPT>
-__global__ void __launch_bounds__(BT, 1) batched_settle_kernel(BatchedK P) {
+template <int TPT, int KQ>
+__global__ void __launch_bounds__(TPT == 3 ? 800 : (TPT == 4 ? 640 : 1024), 1)
+batched_settle_kernel(BatchedK P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = (int)P.N, kq = P.kp / 4;
   float4* p_s = reinterpret_cast<float4*>(smem_raw);                 // [N][2]
   float4* w_s = p_s + (size_t)N * 2;                                  // [N][kq]
-  float4* red = w_s + (size_t)N * kq;                                 // [4][BW*2]
-  ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 4 * BW * 2);      // [N][kq]
+  float4* red = w_s + (size_t)N * kq;                                 // [4][BW_MAX*2]
+  ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 4 * BW_MAX * 2);  // [N][kq]
   float* gates_s = reinterpret_cast<float*>(nbr_s + (size_t)N * kq);  // [N]
   unsigned* flag_s = reinterpret_cast<unsigned*>(gates_s + N);
 
@@ -272,18 +280,41 @@ __global__ void __launch_bounds__(BT, 1) batched_settle_kernel(BatchedK P) {
 
   for (int64_t b = gid; b < P.batch; b += P.groups) {
     __syncthreads();
-    // ---- stage graph + gates
+    // ---- stage graph + gates (one 4-neighbour chunk per thread-iteration, 16 B global loads)
     {
       const int32_t* nb = P.nbr + b * P.N * P.k;
       const float* wt = P.W + b * P.N * P.k;
       const int32_t* dg = P.deg + b * P.N;
-      unsigned short* ns = reinterpret_cast<unsigned short*>(nbr_s);
-      float* ws = reinterpret_cast<float*>(w_s);
-      for (int e = tid; e < N * P.kp; e += BT) {
-        const int row = e / P.kp, t = e - row * P.kp;
-        const bool ok = t < P.k && t < dg[row];
-        ns[e] = (unsigned short)(ok ? nb[(int64_t)row * P.k + t] : row);
-        ws[e] = ok ? wt[(int64_t)row * P.k + t] : 0.f;
+      const bool vec = (P.k & 3) == 0;
+      for (int e = tid; e < N * kq; e += BT) {
+        const int row = e / kq, c = e - row * kq;
+        const int d = dg[row];
+        int j[4];
+        float w[4];
+        if (vec) {
+          const int4 jj = *reinterpret_cast<const int4*>(nb + (int64_t)row * P.k + 4 * c);
+          const float4 ww = *reinterpret_cast<const float4*>(wt + (int64_t)row * P.k + 4 * c);
+          j[0] = jj.x; j[1] = jj.y; j[2] = jj.z; j[3] = jj.w;
+          w[0] = ww.x; w[1] = ww.y; w[2] = ww.z; w[3] = ww.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int t = 4 * c + u;
+            j[u] = t < P.k ? nb[(int64_t)row * P.k + t] : -1;
+            w[u] = t < P.k ? wt[(int64_t)row * P.k + t] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = (4 * c + u) < d;
+          if (!ok) {
+            j[u] = row;  // padding gathers the row itself with weight 0
+            w[u] = 0.f;
+          }
+        }
+        nbr_s[e] = make_ushort4((unsigned short)j[0], (unsigned short)j[1], (unsigned short)j[2],
+                                (unsigned short)j[3]);
+        w_s[e] = make_float4(w[0], w[1], w[2], w[3]);
       }
       for (int e = tid; e < N; e += BT) gates_s[e] = P.gates ? P.gates[b * P.N + e] : 1.0f;
     }
@@ -324,7 +355,7 @@ __global__ void __launch_bounds__(BT, 1) batched_settle_kernel(BatchedK P) {
                                 __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w)));
         }
       }
-      iters = slab_solve<TPT>(st, c, P.tol_settle, P.max_iters_settle, p_s, gates_s, nbr_s, w_s, red,
+      iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, p_s, gates_s, nbr_s, w_s, red,
                               sync_b, P.G, act, &res, flag_s);
       if (Uo != nullptr) {
 #pragma unroll
@@ -361,7 +392,7 @@ __global__ void __launch_bounds__(BT, 1) batched_settle_kernel(BatchedK P) {
               __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
         }
       }
-      iters = slab_solve<TPT>(st, c, P.tol_ustar, P.max_iters_ustar, p_s, gates_s, nbr_s, w_s, red,
+      iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, p_s, gates_s, nbr_s, w_s, red,
                               sync_b + (P.maxit + 1) * 2, P.G, act, &res, flag_s);
       if (P.Ustar_out != nullptr) {
         float* So = P.Ustar_out + b * P.N * P.D;
@@ -394,7 +425,7 @@ __global__ void __launch_bounds__(BT, 1) batched_settle_kernel(BatchedK P) {
         for (int m = 0; m < TPT; ++m) {
           if (act[m]) {
             const int q = tid + BT * m, row = q >> 1;
-            const float4 a = apply_task(p_s, nbr_s, w_s, row, half, kq,
+            const float4 a = apply_task<KQ>(p_s, nbr_s, w_s, row, half, kq,
                                         c.diag0 + c.diag1 * gates_s[row], c.offc);
             part = f4_add(part, f4_mul(p_s[q], a));
           }
@@ -418,17 +449,25 @@ __global__ void batched_dh_reduce_kernel(const double* __restrict__ part, int G,
 }
 
 // ================================================================= host side
+// tasks per thread / threads per CTA: 2N float4 tasks spread over at most 1024 threads, keeping
+// x, r, Ap (12 registers per task) inside the per-thread register budget
 static int tpt_for(int64_t N) {
   const int64_t tasks = 2 * N;
-  if (tasks <= BT) return 1;
-  if (tasks <= 2 * BT) return 2;
-  if (tasks <= 4 * BT) return 4;
+  if (tasks <= 1024) return 1;
+  if (tasks <= 2 * 1024) return 2;
+  if (tasks <= 3 * 800) return 3;
+  if (tasks <= 4 * 640) return 4;
   return 0;
+}
+static int threads_for(int64_t N, int tpt) {
+  int t = (int)((2 * N + tpt - 1) / tpt);
+  t = (t + 31) / 32 * 32;
+  return t < 64 ? 64 : t;
 }
 
 static size_t batched_smem(int64_t N, int k) {
   const int kp = (k + 3) / 4 * 4;
-  return (size_t)N * 32 + (size_t)N * kp * 4 + (size_t)N * kp * 2 + 4 * BW * 2 * 16 + (size_t)N * 4 +
+  return (size_t)N * 32 + (size_t)N * kp * 4 + (size_t)N * kp * 2 + 4 * BW_MAX * 2 * 16 + (size_t)N * 4 +
          16;
 }
 
@@ -489,12 +528,20 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
 
   const size_t smem = batched_smem(g->N, g->k);
   const int tpt = tpt_for(g->N);
+  const int kq = P.kp / 4;
   void* args[] = {&P};
-  const dim3 grid(groups * P.G), block(BT);
+  const dim3 grid(groups * P.G), block(threads_for(g->N, tpt));
   const void* fn = nullptr;
-  if (tpt == 1) fn = (const void*)batched_settle_kernel<1>;
-  else if (tpt == 2) fn = (const void*)batched_settle_kernel<2>;
-  else fn = (const void*)batched_settle_kernel<4>;
+#define OSC_PICK(T)                                                         \
+  (kq == 1 ? (const void*)batched_settle_kernel<T, 1>                        \
+           : kq == 2 ? (const void*)batched_settle_kernel<T, 2>              \
+                     : kq == 4 ? (const void*)batched_settle_kernel<T, 4>    \
+                               : (const void*)batched_settle_kernel<T, 0>)
+  if (tpt == 1) fn = OSC_PICK(1);
+  else if (tpt == 2) fn = OSC_PICK(2);
+  else if (tpt == 3) fn = OSC_PICK(3);
+  else fn = OSC_PICK(4);
+#undef OSC_PICK
   OSC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OSC_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st));
   if (a->do_deltaH) {

@@ -66,7 +66,11 @@ int delta_h(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, const f
             const float*, int, double*, void*, size_t, cudaStream_t);
 int launch_receipt_full(const osc_graph_t*, const osc_params_t*, const float*, const float*,
                         const float*, const float*, int, float, float*, float*, float*, int32_t*,
-                        float*, float*, cudaStream_t);
+                        float*, float*, float*, float*, cudaStream_t);
+int launch_row_align(const float*, const float*, int64_t, int, float*, cudaStream_t);
+int launch_pair_d2(const float*, const float*, const int32_t*, int64_t, int, float*, cudaStream_t);
+size_t mmr_workspace(int64_t N);
+int launch_mmr(const float*, const float*, int64_t, int, int, int32_t*, void*, size_t, cudaStream_t);
 int batched_supported(int64_t, int, int);
 int batched_workspace(int64_t, int64_t, int, size_t*);
 int batched_settle(const osc_graph_t*, const osc_params_t*, const osc_batched_args_t*, void*, size_t,
@@ -309,10 +313,33 @@ int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params
 int osc_receipt_full(const osc_graph_t* g, const osc_params_t* prm, const float* Y, const float* Ustar,
                      const float* psi, const float* gates, int32_t D, float z_th, float* coh,
                      float* anchor, float* query, int32_t* null_j, float* null_z, float* null_R,
-                     void* stream) {
+                     float* row_mu, float* row_sigma, void* stream) {
   OSC_REQUIRE(coh && anchor && query && null_j && null_z && null_R, "receipt_full: NULL output");
   return launch_receipt_full(g, prm, Y, Ustar, psi, gates, D, z_th, coh, anchor, query, null_j, null_z,
-                             null_R, (cudaStream_t)stream);
+                             null_R, row_mu, row_sigma, (cudaStream_t)stream);
+}
+
+int osc_row_align(const float* Ustar, const float* psi, int64_t N, int32_t D, float* align, void* stream) {
+  OSC_REQUIRE(Ustar && psi && align && D >= 1, "row_align: bad argument");
+  return launch_row_align(Ustar, psi, N, D, align, (cudaStream_t)stream);
+}
+
+int osc_pair_d2(const float* V, const float* sqrt_deg, const int32_t* pairs, int64_t M, int32_t D,
+                float* out, void* stream) {
+  OSC_REQUIRE(V && sqrt_deg && (M == 0 || (pairs && out)) && D >= 1, "pair_d2: bad argument");
+  return launch_pair_d2(V, sqrt_deg, pairs, M, D, out, (cudaStream_t)stream);
+}
+
+int osc_mmr_workspace(int64_t N, size_t* h_bytes) {
+  OSC_REQUIRE(h_bytes != nullptr && N >= 0, "mmr_workspace: bad argument");
+  *h_bytes = mmr_workspace(N);
+  return OSC_OK;
+}
+
+int osc_mmr_select(const float* Yn, const float* score, int64_t N, int32_t D, int32_t k, int32_t* chosen,
+                   void* workspace, size_t ws_bytes, void* stream) {
+  OSC_REQUIRE(Yn && score && chosen && D >= 1, "mmr_select: bad argument");
+  return launch_mmr(Yn, score, N, D, k, chosen, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 int osc_batched_supported(int64_t N, int32_t D, int32_t k) { return batched_supported(N, D, k); }

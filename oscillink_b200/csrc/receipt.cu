@@ -20,7 +20,8 @@ receipt_full_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ A
                     const float* __restrict__ gates, float z_th, float* __restrict__ coh,
                     float* __restrict__ anchor, float* __restrict__ query,
                     int32_t* __restrict__ null_j, float* __restrict__ null_z,
-                    float* __restrict__ null_R) {
+                    float* __restrict__ null_R, float* __restrict__ row_mu,
+                    float* __restrict__ row_sigma) {
   const int lane = threadIdx.x & 31;
   const int64_t b = blockIdx.y;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -124,13 +125,15 @@ receipt_full_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ A
     null_j[row] = oj;
     null_z[row] = oz;
     null_R[row] = oR;
+    if (row_mu != nullptr) row_mu[row] = mu;
+    if (row_sigma != nullptr) row_sigma[row] = sigma;
   }
 }
 
 int launch_receipt_full(const osc_graph_t* g, const osc_params_t* prm, const float* Y,
                         const float* Us, const float* psi, const float* gates, int D, float z_th,
                         float* coh, float* anchor, float* query, int32_t* null_j, float* null_z,
-                        float* null_R, cudaStream_t st) {
+                        float* null_R, float* row_mu, float* row_sigma, cudaStream_t st) {
   OSC_REQUIRE(g != nullptr && prm != nullptr && Y != nullptr && Us != nullptr && psi != nullptr,
               "receipt_full: NULL argument");
   if (g->N == 0 || g->batch == 0) return OSC_OK;
@@ -138,7 +141,8 @@ int launch_receipt_full(const osc_graph_t* g, const osc_params_t* prm, const flo
   dim3 grid((unsigned)((g->N + warps - 1) / warps), (unsigned)g->batch);
   receipt_full_kernel<<<grid, warps * 32, 0, st>>>(g->nbr, g->A, g->deg, g->sqrt_deg, g->N, g->k, D,
                                                    prm->lamG, prm->lamC, prm->lamQ, Y, Us, psi, gates,
-                                                   z_th, coh, anchor, query, null_j, null_z, null_R);
+                                                   z_th, coh, anchor, query, null_j, null_z, null_R, row_mu,
+                                                   row_sigma);
   OSC_LAUNCH_CHECK("receipt_full_kernel");
   return OSC_OK;
 }

@@ -528,8 +528,10 @@ class OscillinkLattice:
         )
         return float(np.float32(out.value))
 
-    def _node_terms_device(self, Ustar, z_th: float = 3.0):
+    def _node_terms_device(self, Ustar, z_th: float = 3.0, row_stats: bool = False):
         dev, N = self._dev, self.N
+        mu = torch.zeros(N, dtype=torch.float32, device=dev) if row_stats else None
+        sg = torch.zeros(N, dtype=torch.float32, device=dev) if row_stats else None
         coh = torch.zeros(N, dtype=torch.float32, device=dev)
         anc = torch.zeros(N, dtype=torch.float32, device=dev)
         qry = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -543,9 +545,11 @@ class OscillinkLattice:
                                            Ustar.data_ptr(), self._dpsi.data_ptr(), self._dB.data_ptr(),
                                            self.D, float(z_th), coh.data_ptr(), anc.data_ptr(),
                                            qry.data_ptr(), nj.data_ptr(), nz.data_ptr(), nr.data_ptr(),
-                                           _stream_ptr()),
+                                           _cabi.ptr(mu), _cabi.ptr(sg), _stream_ptr()),
                 "osc_receipt_full",
             )
+        if row_stats:
+            return coh, anc, qry, nj, nz, nr, mu, sg
         return coh, anc, qry, nj, nz, nr
 
     def receipt(self) -> dict[str, Any]:
@@ -639,6 +643,104 @@ class OscillinkLattice:
             meta["dynamics"] = self._last_dynamics
         self._log("receipt", {"deltaH_total": out["deltaH_total"], "ustar_cached": meta["ustar_cached"]})
         return out
+
+    # ------------------------------------------------------------------ chain receipt / bundle (f2, f1)
+    def _pair_d2(self, V, pairs: np.ndarray) -> np.ndarray:
+        """|| V_i/(sd_i+1e-12) - V_j/(sd_j+1e-12) ||^2 for (i,j) rows of `pairs` (device kernel)."""
+        M = int(pairs.shape[0])
+        if M == 0:
+            return np.zeros(0, dtype=_F32)
+        dp = torch.from_numpy(np.ascontiguousarray(pairs, dtype=np.int32)).to(self._dev)
+        out = torch.empty(M, dtype=torch.float32, device=self._dev)
+        _cabi.check(self._lib.osc_pair_d2(V.data_ptr(), self._sd.data_ptr(), dp.data_ptr(), M, self.D,
+                                          out.data_ptr(), _stream_ptr()), "osc_pair_d2")
+        return out.cpu().numpy()
+
+    def _adjacency_lookup(self, i: int, j: int) -> float:
+        nbr = self._nbr[i].cpu().numpy()
+        a = self._A[i].cpu().numpy()
+        hit = np.nonzero(nbr == j)[0]
+        return float(a[hit[0]]) if len(hit) else 0.0
+
+    def chain_receipt(self, chain: list[int], z_th: float = 2.5) -> dict[str, Any]:
+        """Per-chain-edge z-scores, weakest link and coherence gain (lattice.py:466-528).
+
+        The D-dimensional work (pair distances, per-row residual statistics) runs on device; the
+        O(len(chain)) assembly of the verdict is host bookkeeping."""
+        Ustar = self._solve_Ustar_device(1e-4, 64, True)
+        *_, mu_s_d, sig_s_d = self._node_terms_device(Ustar, 3.0, row_stats=True)
+        mu_s, sig_s = mu_s_d.cpu().numpy(), sig_s_d.cpu().numpy()
+        path = self._chain if self._chain is not None else self._make_chain(chain, None)
+        ap = path["ap_host"]
+        edges_p = np.array(sorted(ap.keys()), dtype=np.int32).reshape(-1, 2)
+        d2_p = dict(zip(map(tuple, edges_p.tolist()), self._pair_d2(Ustar, edges_p)))
+        cp = _F32(max(self.lamC, 1e-6))
+        N = self.N
+
+        def path_stats(i: int):
+            vals = np.array([_F32(_F32(cp * ap[(u, v)]) * d2_p[(u, v)]) for (u, v) in ap if u == i],
+                            dtype=_F32)
+            mu = _F32(vals.sum(dtype=_F32) / _F32(N)) if len(vals) else _F32(0)
+            dev = float(((vals.astype(np.float64) - float(mu)) ** 2).sum()) + (N - len(vals)) * float(mu) ** 2
+            return mu, _F32(np.sqrt(dev / N)) + _F32(1e-12)
+
+        pairs = np.array([[int(chain[t]), int(chain[t + 1])] for t in range(len(chain) - 1)],
+                         dtype=np.int32).reshape(-1, 2)
+        d2u = self._pair_d2(Ustar, pairs)
+        d2y = self._pair_d2(self._dY, pairs)
+        edges: list[dict[str, Any]] = []
+        worst = (-1, -1.0, (-1, -1))
+        gain = 0.0
+        for t, (i, j) in enumerate(pairs.tolist()):
+            w_ij = self._adjacency_lookup(i, j)
+            rs = _F32(_F32(_F32(self.lamC) * _F32(w_ij)) * d2u[t])
+            rp = _F32(_F32(cp * ap.get((i, j), _F32(0))) * d2u[t])
+            mu_p, sig_p = path_stats(i)
+            z_struct = float((rs - mu_s[i]) / sig_s[i])
+            z_path = float((rp - mu_p) / sig_p)
+            edges.append({"k": int(t), "edge": [int(i), int(j)], "z_struct": z_struct, "z_path": z_path,
+                          "r_struct": float(rs), "r_path": float(rp)})
+            if max(z_struct, z_path) > worst[1]:
+                worst = (t, max(z_struct, z_path), (i, j))
+            gain += 0.5 * float(self.lamC) * max(w_ij, 0.0) * (float(d2y[t]) - float(d2u[t]))
+        verdict = all(max(e["z_struct"], e["z_path"]) <= float(z_th) for e in edges)
+        return {
+            "verdict": bool(verdict),
+            "weakest_link": {"k": int(worst[0]), "edge": [int(worst[2][0]), int(worst[2][1])],
+                             "zscore": float(worst[1])},
+            "coherence_gain": float(gain),
+            "edges": edges,
+        }
+
+    def bundle(self, k: int = 8, alpha: float = 0.5) -> list[dict]:
+        """Top-k diversified bundle: score = alpha*z(coherence drop) + (1-alpha)*cos(U*_i, psi), then
+        greedy MMR (lambda 0.5) over the anchors (lattice.py:530-568, graph.py:114-133)."""
+        Ustar = self._solve_Ustar_device(1e-4, 64, True)
+        N = self.N
+        align_d = torch.empty(N, dtype=torch.float32, device=self._dev)
+        _cabi.check(self._lib.osc_row_align(Ustar.data_ptr(), self._dpsi.data_ptr(), N, self.D,
+                                            align_d.data_ptr(), _stream_ptr()), "osc_row_align")
+        coh_d = self._node_terms_device(Ustar, 3.0)[0]
+        align, coh = align_d.cpu().numpy(), coh_d.cpu().numpy()
+        mu, sigma = float(np.mean(coh)), float(np.std(coh) + 1e-12)
+        z = (coh - mu) / sigma if sigma > 0 else np.zeros_like(coh)
+        score = (alpha * z + (1 - alpha) * align).astype(_F32)
+        if k <= 0 or N == 0:
+            return []
+        Yn = torch.empty_like(self._dY)
+        _cabi.check(self._lib.osc_normalize_rows(self._dY.data_ptr(), N, self.D, Yn.data_ptr(), None, None,
+                                                 _stream_ptr()), "osc_normalize_rows")
+        score_d = torch.from_numpy(score).to(self._dev)
+        steps = min(int(k), N)
+        chosen = torch.full((steps,), -1, dtype=torch.int32, device=self._dev)
+        need = C.c_size_t(0)
+        _cabi.check(self._lib.osc_mmr_workspace(N, C.byref(need)))
+        ws = self._ws.get(need.value)
+        _cabi.check(self._lib.osc_mmr_select(Yn.data_ptr(), score_d.data_ptr(), N, self.D, steps,
+                                             chosen.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()),
+                    "osc_mmr_select")
+        order = chosen.cpu().numpy().tolist()
+        return [{"id": int(i), "score": float(score[i]), "align": float(align[i])} for i in order]
 
     def verify_current_receipt(self, secret: bytes | str) -> bool:
         from .receipts import verify_receipt

@@ -1,0 +1,475 @@
+"""One lattice sharded over the GPUs of a box (BASELINE.json configs #4/#5).
+
+One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch; gloo also works and is what
+the CPU tests use for the host-side schedule).  Rank g owns the contiguous row block
+[g*S, min(N,(g+1)*S)) with S = ceil(N/G) of Y, U and of the graph.
+
+Build (graph.py:29-93):
+  all-gather the anchor rows -> every rank normalises all N rows with the same kernel (bit-identical
+  Yn everywhere) -> each rank runs the fused similarity/top-k kernel for ITS row panel against all N
+  columns -> canonical rescoring of its rows -> all-gather of the N x k top tables -> every rank
+  assembles the (tiny, O(N k)) mutual/cap/degree arrays for all rows redundantly, so no further
+  exchange of c_j / 1/sd_j is needed.
+
+Solve (solver.py:15-37), two exact partitions of the same recurrences:
+  mode="rows"    (north_star): per iteration the search direction p is all-gathered (the halo
+                 exchange; on kNN graphs of random anchors ~2/3 of every remote shard is needed
+                 anyway), the SpMM runs on local rows, and the per-column dot products
+                 (p.Ap, r.r, r.z: D floats each) are all-reduced.
+  mode="columns" every reduction of the solver is per column, so a rank that owns ALL rows of a
+                 D/G column slab needs no halo and no dot all-reduce -- only a 1-float MAX
+                 all-reduce for the stop test.  Results are identical.
+
+The per-iteration kernels are the exported phase entry points of the C ABI (osc_pcg_*).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Any
+
+import numpy as np
+
+__all__ = ["ShardedLattice", "shard_bounds", "gather_rows", "pcg_schedule"]
+
+
+# ----------------------------------------------------------------------------- partition helpers
+def shard_bounds(N: int, world: int, rank: int) -> tuple[int, int, int]:
+    """(row0, n_local, shard) for the contiguous block partition with shard = ceil(N/world)."""
+    shard = (N + world - 1) // world if world > 0 else N
+    row0 = min(N, rank * shard)
+    return row0, max(0, min(N, row0 + shard) - row0), shard
+
+
+def gather_rows(local, N: int, group=None):
+    """All-gather row blocks of the block partition into the full [N, ...] tensor (every rank).
+    Blocks are padded to the common shard size so a plain all_gather_into_tensor applies."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local[:N]
+    rank = dist.get_rank(group)
+    _, n_loc, shard = shard_bounds(N, world, rank)
+    assert local.shape[0] == n_loc, (local.shape, n_loc)
+    tail = tuple(local.shape[1:])
+    padded = local
+    if n_loc < shard:
+        padded = torch.zeros((shard,) + tail, dtype=local.dtype, device=local.device)
+        padded[:n_loc] = local
+    if padded.is_cuda and dist.get_backend(group) == "gloo":
+        # gloo has no CUDA all_gather: stage through the host (single-GPU test rigs only;
+        # production runs use NCCL)
+        host = torch.empty((world * shard,) + tail, dtype=local.dtype)
+        dist.all_gather_into_tensor(host, padded.cpu().contiguous(), group=group)
+        return host.to(local.device)[:N]
+    out = torch.empty((world * shard,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    return out[:N]
+
+
+def _allreduce(t, op, group=None):
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=op, group=group)
+    return t
+
+
+def pcg_schedule(k, *, mode: str, tol: float, max_iters: int, group=None):
+    """The distributed PCG driver (solver.py:19-37) written against a kernel facade `k`:
+
+        k.residual0(x_all) -> None          r = b - A x ; p = precond(r); fills k.part_rz
+        k.reduce(which)    -> tensor[D]     column sums of the named partial ("rz","pap","rr","rz_new")
+        k.spmm(p_all)      -> None          Ap = A p ; fills part_pap
+        k.update(rz, pap)  -> None          x += alpha p ; r -= alpha Ap ; fills part_rr, part_rz_new
+        k.pupdate(rz_new, rz) -> None       p = z + beta p
+        k.p_local() / k.x_local()           local row blocks (mode rows) or column slabs
+
+    Returns (iters, res).  `mode` selects which collectives sit between the phases."""
+    import torch
+    import torch.distributed as dist
+
+    rows = mode == "rows"
+    SUM, MAX = dist.ReduceOp.SUM, dist.ReduceOp.MAX
+
+    def full(vec):
+        return gather_rows(vec, k.N, group) if rows else vec
+
+    def colsum(which):
+        s = k.reduce(which)
+        return _allreduce(s, SUM, group) if rows else s
+
+    k.residual0(full(k.x_local()))
+    rz = colsum("rz").clone()
+    it, res = 0, float("nan")
+    for it in range(1, max_iters + 1):
+        k.spmm(full(k.p_local()))
+        pap = colsum("pap")
+        k.update(rz, pap)
+        if rows:
+            both = torch.stack([k.reduce("rr"), k.reduce("rz_new")])
+            _allreduce(both, SUM, group)
+            rr, rz_new = both[0], both[1]
+            res = float(torch.sqrt(torch.clamp(rr.max(), min=0)).item())
+        else:
+            rr, rz_new = k.reduce("rr"), k.reduce("rz_new")
+            m = torch.sqrt(torch.clamp(rr.max(), min=0)).reshape(1)
+            res = float(_allreduce(m, MAX, group).item())
+        if res <= tol or it == max_iters:
+            break
+        k.pupdate(rz_new, rz)
+        rz = rz_new.clone()
+    return it, res
+
+
+# ----------------------------------------------------------------------------- native kernel facade
+class _NativeKernels:
+    """osc_pcg_* phase calls for one (rows | columns) partition on the current device."""
+
+    def __init__(self, lat: "ShardedLattice", mode_id: int, dt: float, jacobi: bool, X, Bv):
+        import torch
+
+        from . import _cabi
+
+        self.cabi, self.lib, self.lat = _cabi, lat._lib, lat
+        self.N = lat.N
+        self.mode_id, self.dt, self.jacobi = mode_id, float(dt), 1 if jacobi else 0
+        dev = lat._dev
+        if lat.mode == "rows":
+            self.dims = _cabi.PcgDims(lat.N, lat.row0, lat.n_local, lat.D, 0)
+            self.graph = lat._graph_struct(local=True)
+            self.gates = lat._dB_loc
+            self.Dl = lat.D
+        else:
+            self.dims = _cabi.PcgDims(lat.N, 0, lat.N, lat.Dl, 0)
+            self.graph = lat._graph_struct(local=False)
+            self.gates = lat._dB_all
+            self.Dl = lat.Dl
+        need = C.c_size_t(0)
+        _cabi.check(self.lib.osc_pcg_plan(C.byref(self.dims), C.byref(need)))
+        nb, Dl = self.dims.n_blocks, self.Dl
+        self.X, self.R = X, Bv
+        self.P = torch.empty_like(X)
+        self.AP = torch.empty_like(X)
+        self.parts = {n: torch.zeros((nb, Dl), dtype=torch.float64, device=dev)
+                      for n in ("rz", "pap", "rr", "rz_new")}
+        self.out = {n: torch.zeros(Dl, dtype=torch.float32, device=dev) for n in self.parts}
+        self.prm = lat._params_struct()
+        self.chain = lat._chain_struct()
+
+    def _st(self):
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+
+    def _chain_arg(self):
+        return C.byref(self.chain) if self.chain is not None else None
+
+    def x_local(self):
+        return self.X
+
+    def p_local(self):
+        return self.P
+
+    def residual0(self, x_all):
+        self.cabi.check(self.lib.osc_pcg_residual0(
+            C.byref(self.dims), C.byref(self.graph), self._chain_arg(), C.byref(self.prm), self.mode_id,
+            self.dt, self.jacobi, self.gates.data_ptr(), x_all.data_ptr(), self.R.data_ptr(),
+            self.P.data_ptr(), self.parts["rz"].data_ptr(), self._st()), "osc_pcg_residual0")
+
+    def spmm(self, p_all):
+        self.cabi.check(self.lib.osc_pcg_spmm_dot(
+            C.byref(self.dims), C.byref(self.graph), self._chain_arg(), C.byref(self.prm), self.mode_id,
+            self.dt, self.gates.data_ptr(), p_all.data_ptr(), self.AP.data_ptr(),
+            self.parts["pap"].data_ptr(), self._st()), "osc_pcg_spmm_dot")
+
+    def reduce(self, which):
+        self.cabi.check(self.lib.osc_pcg_reduce(self.parts[which].data_ptr(), self.dims.n_blocks, self.Dl,
+                                                self.out[which].data_ptr(), None, self._st()),
+                        "osc_pcg_reduce")
+        return self.out[which]
+
+    def update(self, rz, pap):
+        self.cabi.check(self.lib.osc_pcg_update(
+            C.byref(self.dims), C.byref(self.prm), self.mode_id, self.dt, self.jacobi,
+            self.gates.data_ptr(), rz.data_ptr(), pap.data_ptr(), self.P.data_ptr(), self.AP.data_ptr(),
+            self.X.data_ptr(), self.R.data_ptr(), self.parts["rr"].data_ptr(),
+            self.parts["rz_new"].data_ptr(), self._st()), "osc_pcg_update")
+
+    def pupdate(self, rz_new, rz_old):
+        self.cabi.check(self.lib.osc_pcg_pupdate(
+            C.byref(self.dims), C.byref(self.prm), self.mode_id, self.dt, self.jacobi,
+            self.gates.data_ptr(), rz_new.data_ptr(), rz_old.data_ptr(), self.R.data_ptr(),
+            self.P.data_ptr(), self._st()), "osc_pcg_pupdate")
+
+
+# ----------------------------------------------------------------------------- the lattice
+class ShardedLattice:
+    """Row-sharded lattice.  `Y_local` is this rank's row block (see shard_bounds)."""
+
+    def __init__(self, Y_local, N: int, kneighbors: int = 6, row_cap_val: float = 1.0, lamG: float = 1.0,
+                 lamC: float = 0.5, lamQ: float = 4.0, *, mode: str = "rows", group=None,
+                 knn_engine: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        from . import _cabi
+
+        if mode not in {"rows", "columns"}:
+            raise ValueError("mode must be 'rows' or 'columns'")
+        if kneighbors < 1:
+            raise ValueError("kneighbors must be >= 1")
+        if lamG <= 0:
+            raise ValueError("lamG must be > 0 for SPD")
+        if lamC < 0 or lamQ < 0:
+            raise ValueError("lamC and lamQ must be >= 0")
+        if not torch.cuda.is_available():
+            raise RuntimeError("oscillink_b200 needs a CUDA device (sm_100a); no CPU fallback")
+        self._cabi, self._lib = _cabi, _cabi.load()
+        self._dev = torch.device("cuda", torch.cuda.current_device())
+        self.group, self.mode = group, mode
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.N = int(N)
+        self.row0, self.n_local, self.shard = shard_bounds(self.N, self.world, self.rank)
+        if isinstance(Y_local, np.ndarray):
+            Y_local = torch.from_numpy(np.ascontiguousarray(Y_local, dtype=np.float32))
+        Y_local = Y_local.to(self._dev, dtype=torch.float32).contiguous()
+        if Y_local.ndim != 2 or Y_local.shape[0] != self.n_local:
+            raise ValueError(f"Y_local must hold this rank's {self.n_local} rows")
+        self.D = int(Y_local.shape[1])
+        if mode == "columns":
+            if self.D % (4 * self.world) != 0:
+                raise ValueError("mode='columns' needs D divisible by 4*world_size")
+            self.Dl = self.D // self.world
+            self.c0 = self.rank * self.Dl
+        self.k = min(int(kneighbors), max(1, self.N - 1))
+        self.row_cap_val = float(row_cap_val)
+        self.lamG, self.lamC, self.lamQ, self.lamP = float(lamG), float(lamC), float(lamQ), 0.0
+        self._chain = None
+        self._chain_nodes = None
+        self._engine = knn_engine
+        self.last: dict[str, Any] = {"iters": 0, "res": None, "t_ms": None}
+        self.timings: dict[str, float] = {}
+        self._build(Y_local)
+        self._dB_all = torch.ones(self.N, dtype=torch.float32, device=self._dev)
+        self._dB_loc = self._dB_all[self.row0:self.row0 + self.n_local]
+        self._dpsi = torch.zeros(self.D, dtype=torch.float32, device=self._dev)
+        self._Ustar = None
+
+    # ---- local views of the state: rows mode [n_local, D]; columns mode [N, D/G]
+    def _slab(self, full):
+        return full[:, self.c0:self.c0 + self.Dl].contiguous()
+
+    def _build(self, Y_local) -> None:
+        import torch
+
+        cabi, lib, dev = self._cabi, self._lib, self._dev
+        N, D, k = self.N, self.D, self.k
+        t0 = time.time()
+        Y_all = gather_rows(Y_local, N, self.group).contiguous()
+        st = torch.cuda.current_stream().cuda_stream
+        nbr = torch.full((N, k), -1, dtype=torch.int32, device=dev)
+        A = torch.zeros((N, k), dtype=torch.float32, device=dev)
+        W = torch.zeros((N, k), dtype=torch.float32, device=dev)
+        deg = torch.zeros(N, dtype=torch.int32, device=dev)
+        sd = torch.full((N,), 1e-6, dtype=torch.float32, device=dev)
+        self.nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        if N >= 2:
+            kc = min(k + 4, N - 1)
+            use_tc = (self._engine != cabi.KNN_SIMT and bool(lib.osc_knn_tc_supported(N, D, kc))
+                      and (self._engine == cabi.KNN_TC or N >= 256))
+            Yn = torch.empty_like(Y_all)
+            hi = torch.empty_like(Y_all) if use_tc else None
+            lo = torch.empty_like(Y_all) if use_tc else None
+            P = cabi.ptr
+            cabi.check(lib.osc_normalize_rows(Y_all.data_ptr(), N, D, Yn.data_ptr(), P(hi), P(lo), st))
+            nl, r0 = self.n_local, self.row0
+            cand_idx = torch.empty((max(nl, 1), kc), dtype=torch.int32, device=dev)
+            cand_sim = torch.empty((max(nl, 1), kc), dtype=torch.float32, device=dev)
+            top_idx = torch.full((max(nl, 1), k), -1, dtype=torch.int32, device=dev)
+            top_sim = torch.zeros((max(nl, 1), k), dtype=torch.float32, device=dev)
+            gap = torch.empty(max(nl, 1), dtype=torch.float32, device=dev)
+            if nl > 0:
+                off = r0 * D * 4
+                q = lambda t: None if t is None else t.data_ptr() + off  # noqa: E731
+                cabi.check(lib.osc_knn_candidates(
+                    q(Yn), Yn.data_ptr(), q(hi), q(lo), P(hi), P(lo), 1, nl, r0, N, D, kc,
+                    cabi.KNN_TC if use_tc else cabi.KNN_SIMT, cand_idx.data_ptr(), cand_sim.data_ptr(),
+                    None, 0, st), "osc_knn_candidates")
+                cabi.check(lib.osc_knn_rescore(q(Yn), Yn.data_ptr(), 1, nl, N, D, cand_idx.data_ptr(), kc,
+                                               k, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
+                                               st), "osc_knn_rescore")
+            self.gap_local = gap[:nl]
+            top_idx_all = gather_rows(top_idx[:nl], N, self.group).contiguous()
+            top_sim_all = gather_rows(top_sim[:nl], N, self.group).contiguous()
+            scratch = torch.empty(N, dtype=torch.float32, device=dev)
+            cabi.check(lib.osc_graph_assemble(top_idx_all.data_ptr(), top_sim_all.data_ptr(), 1, N, k,
+                                              self.row_cap_val, nbr.data_ptr(), A.data_ptr(),
+                                              W.data_ptr(), deg.data_ptr(), sd.data_ptr(),
+                                              self.nnz.data_ptr(), scratch.data_ptr(), st),
+                       "osc_graph_assemble")
+            del Yn, hi, lo
+        self._nbr, self._A, self._W, self._deg, self._sd = nbr, A, W, deg, sd
+        if self.mode == "rows":
+            self._Y = Y_local
+            del Y_all
+        else:
+            self._Y = self._slab(Y_all)
+            del Y_all
+        self._U = self._Y.clone()
+        torch.cuda.current_stream().synchronize()
+        self.timings["graph_build_ms"] = 1000.0 * (time.time() - t0)
+
+    # ---- C-ABI structs
+    def _graph_struct(self, local: bool):
+        g = self._cabi.Graph
+        if local:
+            r0, r1 = self.row0, self.row0 + self.n_local
+            return g(1, self.n_local, self.k, 0, self._nbr[r0:r1].data_ptr() if self.n_local else 0,
+                     self._A[r0:r1].data_ptr() if self.n_local else 0,
+                     self._W[r0:r1].data_ptr() if self.n_local else 0,
+                     self._deg[r0:r1].data_ptr() if self.n_local else 0,
+                     self._sd[r0:r1].data_ptr() if self.n_local else 0)
+        return g(1, self.N, self.k, 0, self._nbr.data_ptr(), self._A.data_ptr(), self._W.data_ptr(),
+                 self._deg.data_ptr(), self._sd.data_ptr())
+
+    def _params_struct(self):
+        return self._cabi.Params(self.lamG, self.lamC, self.lamQ, self.lamP,
+                                 1 if self._chain is not None else 0, 0)
+
+    def _chain_struct(self):
+        if self._chain is None:
+            return None
+        c = self._chain
+        return self._cabi.Chain(c["n_rows"], c["nnz"], c["rows"].data_ptr(), c["rowptr"].data_ptr(),
+                                c["col"].data_ptr(), c["Wp"].data_ptr(), c["Ap"].data_ptr(),
+                                c["slot"].data_ptr())
+
+    # ---- public API (subset of OscillinkLattice that makes sense for a sharded lattice)
+    def set_query(self, psi, gates=None) -> None:
+        import torch
+
+        self._dpsi = torch.as_tensor(np.asarray(psi, dtype=np.float32)).to(self._dev)
+        if gates is not None:
+            g = torch.as_tensor(np.asarray(gates, dtype=np.float32))
+            if g.shape[0] != self.N:
+                raise ValueError("gates length mismatch N")
+            self._dB_all = g.to(self._dev)
+            self._dB_loc = self._dB_all[self.row0:self.row0 + self.n_local]
+        self._Ustar = None
+
+    def add_chain(self, chain, lamP: float = 0.2, weights=None) -> None:
+        from .lattice_api import OscillinkLattice
+
+        if lamP < 0:
+            raise ValueError("lamP must be >= 0")
+        if any((c < 0 or c >= self.N) for c in chain):
+            raise ValueError("chain indices out of bounds")
+        if len(chain) < 2:
+            raise ValueError("chain must contain at least two indices")
+        if weights is not None and len(weights) != len(chain) - 1:
+            raise ValueError("weights length must equal len(chain)-1")
+        self._chain = OscillinkLattice._make_chain(self, chain, weights)  # same CSR builder
+        self.lamP = float(lamP)
+        self._chain_nodes = list(map(int, chain))
+        self._Ustar = None
+
+    def _psi_view(self):
+        return self._dpsi if self.mode == "rows" else self._dpsi[self.c0:self.c0 + self.Dl].contiguous()
+
+    def _solve(self, mode_id: int, dt: float, tol: float, max_iters: int, jacobi: bool = True,
+               warm_start: bool = True, inertia: float = 0.0):
+        import torch
+
+        cabi, lib = self._cabi, self._lib
+        rows = self.mode == "rows"
+        X = torch.empty_like(self._Y)
+        Bv = torch.empty_like(self._Y)
+        Dl = self.D if rows else self.Dl
+        n_loc = self.n_local if rows else self.N
+        dims = cabi.PcgDims(self.N, self.row0 if rows else 0, n_loc, Dl, 0)
+        prm = self._params_struct()
+        gates = self._dB_loc if rows else self._dB_all
+        psi = self._psi_view()
+        if n_loc > 0:
+            cabi.check(lib.osc_pcg_setup(C.byref(dims), C.byref(prm), mode_id, float(dt),
+                                         1 if warm_start else 0, float(inertia), self._Y.data_ptr(),
+                                         self._U.data_ptr(), psi.data_ptr(), gates.data_ptr(),
+                                         X.data_ptr(), Bv.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "osc_pcg_setup")
+        k = _NativeKernels(self, mode_id, dt, jacobi, X, Bv)
+        it, res = pcg_schedule(k, mode=self.mode, tol=tol, max_iters=max_iters, group=self.group)
+        return X, it, res
+
+    def settle(self, dt: float = 1.0, max_iters: int = 12, tol: float = 1e-3, precond: str = "jacobi", *,
+               warm_start: bool = True, inertia: float = 0.0) -> dict[str, Any]:
+        import torch
+
+        t0 = time.time()
+        X, it, res = self._solve(self._cabi.MODE_SETTLE, dt, tol, max_iters, precond == "jacobi",
+                                 warm_start, inertia)
+        self._U = X
+        torch.cuda.current_stream().synchronize()
+        self.last = {"iters": int(it), "res": float(res), "t_ms": 1000.0 * (time.time() - t0)}
+        return self.last
+
+    def solve_Ustar(self, tol: float = 1e-4, max_iters: int = 64):
+        if self._Ustar is None:
+            X, it, res = self._solve(self._cabi.MODE_STATIONARY, 0.0, tol, max_iters)
+            self._Ustar = X
+            self.last_ustar = {"iters": int(it), "res": float(res), "converged": bool(res <= tol)}
+        return self._Ustar
+
+    def deltaH(self) -> float:
+        """receipts.py:21-25 over the sharded state: <U-U*, M(U-U*)> summed over ranks."""
+        import torch
+        import torch.distributed as dist
+
+        Us = self.solve_Ustar()
+        diff = self._U - Us
+        k = _NativeKernels(self, self._cabi.MODE_STATIONARY, 0.0, True, diff, torch.empty_like(diff))
+        full = gather_rows(diff, self.N, self.group).contiguous() if self.mode == "rows" else diff
+        k.spmm(full)
+        tot = k.parts["pap"].sum().reshape(1)
+        _allreduce(tot, dist.ReduceOp.SUM, self.group)
+        return float(np.float32(tot.item()))
+
+    def receipt(self) -> dict[str, Any]:
+        """Light receipt (lattice.py:298-318,427-439): deltaH + solve statistics."""
+        dH = self.deltaH()
+        lu = getattr(self, "last_ustar", {})
+        return {
+            "deltaH_total": dH, "cg_iters": int(self.last.get("iters") or 0),
+            "residual": float(self.last.get("res") or 0.0), "t_ms": float(self.last.get("t_ms") or 0.0),
+            "meta": {"ustar_iters": int(lu.get("iters", 0)), "ustar_res": float(lu.get("res", 0.0)),
+                     "ustar_converged": bool(lu.get("converged", True)),
+                     "graph_build_ms": float(self.timings.get("graph_build_ms", 0.0)),
+                     "avg_degree": float(int((self._A > 0).sum().item()) / max(self.N, 1)),
+                     "world_size": self.world, "partition": self.mode},
+        }
+
+    # ---- host views for tests / callers
+    def U_full(self) -> np.ndarray:
+        """The settled state gathered on every rank as a host array (N, D)."""
+        return self._gather_state(self._U)
+
+    def Ustar_full(self) -> np.ndarray:
+        return self._gather_state(self.solve_Ustar())
+
+    def _gather_state(self, t) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+
+        if self.mode == "rows":
+            return gather_rows(t, self.N, self.group).cpu().numpy()
+        if self.world == 1:
+            return t.cpu().numpy()
+        src = t.contiguous()
+        if dist.get_backend(self.group) == "gloo":
+            src = src.cpu()
+        parts = [torch.empty_like(src) for _ in range(self.world)]
+        dist.all_gather(parts, src, group=self.group)
+        return torch.cat(parts, dim=1).cpu().numpy()

@@ -291,3 +291,53 @@ def test_tc_and_simt_engines_build_identical_graphs(shape):
         res[name] = (nbr.cpu().numpy(), A.cpu().numpy(), W.cpu().numpy(), nnz.cpu().numpy())
     for a, b in zip(res["simt"], res["tc"]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["quickstart_120", "readme_80", "config2_1200", "gates_300"])
+def test_bundle_matches_reference(api, name):
+    """f1: bundle() ids identical, scores / alignments within 1e-4 (z-scores amplify fp32 noise)."""
+    g, _ = load_golden(name)
+    c = cases.build(name)
+    lat = _make(api, c)
+    lat.settle(**c["settle_kw"])
+    if c["second_settle"]:
+        lat.settle(**c["second_settle"])
+    out = lat.bundle(k=c["bundle_k"])
+    assert [e["id"] for e in out] == [e["id"] for e in g["bundle"]]
+    np.testing.assert_allclose([e["score"] for e in out], [e["score"] for e in g["bundle"]], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose([e["align"] for e in out], [e["align"] for e in g["bundle"]], rtol=2e-4, atol=2e-6)
+    assert lat.bundle(k=0) == []
+
+
+@pytest.mark.parametrize("name", ["quickstart_120", "perf_400", "gates_300"])
+def test_chain_receipt_matches_reference(api, name):
+    """f2: chain_receipt() verdict, weakest link and per-edge z-scores."""
+    g, _ = load_golden(name)
+    c = cases.build(name)
+    lat = _make(api, c)
+    lat.settle(**c["settle_kw"])
+    if c["second_settle"]:
+        lat.settle(**c["second_settle"])
+    cr = lat.chain_receipt(c["chain"])
+    ref = g["chain_receipt"]
+    assert cr["verdict"] == ref["verdict"]
+    assert cr["weakest_link"]["k"] == ref["weakest_link"]["k"]
+    assert cr["weakest_link"]["edge"] == ref["weakest_link"]["edge"]
+    assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < 1e-4
+    assert abs(cr["coherence_gain"] - ref["coherence_gain"]) <= 1e-4 * max(1.0, abs(ref["coherence_gain"]))
+    for a, b in zip(cr["edges"], ref["edges"]):
+        assert a["edge"] == b["edge"]
+        for key in ("z_struct", "z_path", "r_struct", "r_path"):
+            assert abs(a[key] - b[key]) <= 1e-4 * max(1.0, abs(b[key])), (key, a, b)
+
+
+def test_perf_snapshot_weakest_link(api):
+    """The reference's own perf_snapshot.json pins the chain verdict of the N=400 benchmark."""
+    ref = artefacts()["perf_400"]
+    c = cases.build("perf_400")
+    lat = _make(api, c)
+    lat.settle(**c["settle_kw"])
+    cr = lat.chain_receipt(c["chain"])
+    assert cr["verdict"] == ref["chain_verdict"]
+    assert cr["weakest_link"]["edge"] == ref["weakest_link"]["edge"]
+    assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < 1e-4
