@@ -115,6 +115,15 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
+        path = os.environ.get("OSC_B200_LIB")  # dev-only: A/B a previously built variant
+        if path:
+            lib = C.CDLL(path)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+            return _lib
         path = _build.LIB
         if not os.path.exists(path) or (_build.is_stale() and os.path.exists(_build.NVCC)):
             _build.build()
