@@ -226,13 +226,17 @@ int osc_mmr_select(const float* Yn, const float* score, int64_t N, int32_t D, in
                    void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ K3: batched serving
- * One persistent kernel settles `batch` independent lattices of equal (N, D, k):
- * each CTA owns an 8-column slab of one lattice with the CG vectors in registers/shared
- * memory.  do_settle: U_out = settle(U_in or Y).  do_ustar: Ustar_out = stationary solve.
+ * One persistent kernel settles `batch` independent lattices of equal (N, D, k): each CTA
+ * owns a 4-column slab of one lattice with the CG vectors in registers/shared memory and
+ * iterates with no cross-CTA synchronisation; the lattice-wide stop test (solver.py:29-31)
+ * is resolved afterwards (slabs that stopped early are re-run for the lattice's count).
+ * do_settle: U_out = settle(U_in or Y).  do_ustar: Ustar_out = stationary solve.
  * do_deltaH: deltaH[b] = <U_out - Ustar, M (U_out - Ustar)> (needs both).
  * psi: [batch][D]; gates: [batch][N] or NULL (= ones).  stats: [batch][4] floats
- * {settle_iters, settle_res, ustar_iters, ustar_res}.  sync_ws: zero-initialised by the
- * call; size from osc_batched_workspace. */
+ * {settle_iters, settle_res, ustar_iters, ustar_res}.  unresolved (optional): [batch] int32
+ * flags -- bit 0: the per-slab residuals were not monotone around the stop and the lattice
+ * must be settled with osc_pcg_solve instead (never seen on real inputs; the host mirror
+ * handles it); bit 1 (informational): some slab of the lattice was re-run in pass 2. */
 typedef struct osc_batched_args {
   const float* Y;
   const float* U_in; /* NULL -> Y */
@@ -247,6 +251,7 @@ typedef struct osc_batched_args {
   float dt;
   double tol_settle, tol_ustar;
   int32_t max_iters_settle, max_iters_ustar;
+  int32_t* unresolved; /* [batch] or NULL */
 } osc_batched_args_t;
 
 int osc_batched_supported(int64_t N, int32_t D, int32_t k);

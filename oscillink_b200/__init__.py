@@ -18,7 +18,7 @@ def __getattr__(name):  # lazy: torch / the native library load only when the AP
         from . import lattice_api
 
         return getattr(lattice_api, name)
-    if name in {"BatchedLattices"}:
+    if name in {"BatchedLattices", "settle_host_batch"}:
         from . import batched_api
 
         return getattr(batched_api, name)
@@ -29,5 +29,5 @@ def __getattr__(name):  # lazy: torch / the native library load only when the AP
     raise AttributeError(name)
 
 
-__all__ = ["OscillinkLattice", "Oscillink", "BatchedLattices", "ShardedLattice", "verify_receipt",
+__all__ = ["OscillinkLattice", "Oscillink", "BatchedLattices", "settle_host_batch", "ShardedLattice", "verify_receipt",
            "verify_receipt_mode", "json_line_logger", "__version__"]

@@ -46,7 +46,7 @@ class BatchedArgs(C.Structure):
                 ("U_out", c_void_p), ("Ustar_out", c_void_p), ("stats", c_void_p), ("deltaH", c_void_p),
                 ("D", c_i32), ("do_settle", c_i32), ("do_ustar", c_i32), ("do_deltaH", c_i32),
                 ("dt", c_f32), ("tol_settle", c_f64), ("tol_ustar", c_f64),
-                ("max_iters_settle", c_i32), ("max_iters_ustar", c_i32)]
+                ("max_iters_settle", c_i32), ("max_iters_ustar", c_i32), ("unresolved", c_void_p)]
 
 
 P = C.POINTER

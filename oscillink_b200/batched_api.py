@@ -21,7 +21,7 @@ import torch
 from . import _cabi
 from ._cabi import BatchedArgs, Graph, Params
 
-__all__ = ["BatchedLattices"]
+__all__ = ["BatchedLattices", "settle_host_batch"]
 
 
 class BatchedLattices:
@@ -54,6 +54,7 @@ class BatchedLattices:
         self.psi = torch.zeros((self.B, self.D), dtype=torch.float32, device=self._dev)
         self.gates = None
         self.U = None
+        self._U_prev = None
         self.Ustar = None
         self._build()
 
@@ -148,12 +149,19 @@ class BatchedLattices:
         return bool(self._lib.osc_batched_supported(self.N, self.D, self.k))
 
     def settle(self, dt: float = 1.0, max_iters: int = 12, tol: float = 1e-3, *, receipt: bool = True,
-               ustar_tol: float = 1e-4, ustar_max_iters: int = 64, keep_ustar: bool = False
-               ) -> dict[str, Any]:
+               ustar_tol: float = 1e-4, ustar_max_iters: int = 64, keep_ustar: bool = False,
+               strict: bool = True) -> dict[str, Any]:
         """settle() [+ light receipt()] for every lattice, one persistent kernel launch.
 
         Returns device tensors: iters[B], res[B] and, with receipt=True, ustar_iters[B],
-        ustar_res[B], deltaH[B] (float64)."""
+        ustar_res[B], deltaH[B] (float64), plus unresolved[B] (int32 flags: bit 0 = needs the
+        fallback below, bit 1 = some slab was re-run by the kernel's own fix pass).
+
+        The slab kernel resolves the lattice-wide stop test after the fact; a lattice whose
+        per-slab residuals are not monotone around the stop is flagged in `unresolved`.  With
+        strict=True (default) the call synchronises, and flagged lattices are settled again
+        with the HBM-resident PCG (osc_pcg_solve) so every returned row is final; strict=False
+        returns without synchronising and leaves that to `resolve_flagged(out)`."""
         if not self.supported():
             raise _cabi.OscillinkNativeError(
                 "batched kernel does not cover this shape; use OscillinkLattice per lattice")
@@ -162,6 +170,7 @@ class BatchedLattices:
         U_out = torch.empty_like(self.Y)
         stats = torch.zeros((B, 4), dtype=torch.float32, device=dev)
         dH = torch.zeros(B, dtype=torch.float64, device=dev)
+        unres = torch.zeros(B, dtype=torch.int32, device=dev)
         Us = torch.empty_like(self.Y) if (receipt and keep_ustar) else None
         g = Graph(B, self.N, self.k, 0, self.nbr.data_ptr(), self.A.data_ptr(), self.W.data_ptr(),
                   self.deg.data_ptr(), self.sqrt_deg.data_ptr())
@@ -169,7 +178,7 @@ class BatchedLattices:
         args = BatchedArgs(self.Y.data_ptr(), _cabi.ptr(U_in), self.psi.data_ptr(), _cabi.ptr(self.gates),
                            U_out.data_ptr(), _cabi.ptr(Us), stats.data_ptr(), dH.data_ptr(), self.D,
                            1, 1 if receipt else 0, 1 if receipt else 0, float(dt), float(tol),
-                           float(ustar_tol), int(max_iters), int(ustar_max_iters))
+                           float(ustar_tol), int(max_iters), int(ustar_max_iters), unres.data_ptr())
         need = C.c_size_t(0)
         _cabi.check(self._lib.osc_batched_workspace(B, self.N, self.D, C.byref(need)))
         ws = self._workspace(need.value)
@@ -182,9 +191,124 @@ class BatchedLattices:
         )
         e1.record()
         self.events["batched_settle"] = (e0, e1)
+        self._U_prev = U_in
         self.U = U_out
         self.Ustar = Us
-        out = {"iters": stats[:, 0], "res": stats[:, 1]}
+        out = {"iters": stats[:, 0], "res": stats[:, 1], "unresolved": unres, "_stats": stats}
         if receipt:
             out.update({"ustar_iters": stats[:, 2], "ustar_res": stats[:, 3], "deltaH": dH})
+        self._last_call = dict(dt=float(dt), max_iters=int(max_iters), tol=float(tol), receipt=bool(receipt),
+                               ustar_tol=float(ustar_tol), ustar_max_iters=int(ustar_max_iters))
+        if strict:
+            self.resolve_flagged(out)
         return out
+
+    def resolve_flagged(self, out: dict[str, Any]) -> int:
+        """Synchronise and settle every lattice flagged `unresolved` with the HBM-resident PCG
+        (csrc/pcg.cu: global stop test every iteration).  Returns how many were redone."""
+        flagged = torch.nonzero(out["unresolved"] & 1).flatten().tolist()
+        if not flagged:
+            return 0
+        a = self._last_call
+        lib, D, N = self._lib, self.D, self.N
+        prm = Params(self.lamG, self.lamC, self.lamQ, 0.0, 0, 0)
+        dims = _cabi.PcgDims(N, 0, N, D, 0)
+        need = C.c_size_t(0)
+        _cabi.check(lib.osc_pcg_plan(C.byref(dims), C.byref(need)))
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self._dev)
+        ones = torch.ones(N, dtype=torch.float32, device=self._dev)
+        stats = out["_stats"]
+        for b in flagged:
+            g = Graph(1, N, self.k, 0, self.nbr[b].data_ptr(), self.A[b].data_ptr(), self.W[b].data_ptr(),
+                      self.deg[b].data_ptr(), self.sqrt_deg[b].data_ptr())
+            gates = self.gates[b] if self.gates is not None else ones
+            U0 = self._U_prev[b] if self._U_prev is not None else self.Y[b]
+            it, res = C.c_int32(0), C.c_float(0.0)
+            X = torch.empty_like(self.Y[b])
+            _cabi.check(lib.osc_pcg_solve(C.byref(g), None, C.byref(prm), _cabi.MODE_SETTLE, a["dt"], 1, 0.0,
+                                          1, a["tol"], a["max_iters"], self.Y[b].data_ptr(), U0.data_ptr(),
+                                          self.psi[b].data_ptr(), gates.data_ptr(), D, X.data_ptr(),
+                                          C.byref(it), C.byref(res), ws.data_ptr(), ws.numel(),
+                                          self._stream()), "osc_pcg_solve")
+            self.U[b].copy_(X)
+            stats[b, 0], stats[b, 1] = float(it.value), float(res.value)
+            if a["receipt"]:
+                Xs = torch.empty_like(self.Y[b])
+                _cabi.check(lib.osc_pcg_solve(C.byref(g), None, C.byref(prm), _cabi.MODE_STATIONARY, 0.0, 0,
+                                              0.0, 1, a["ustar_tol"], a["ustar_max_iters"],
+                                              self.Y[b].data_ptr(), self.Y[b].data_ptr(),
+                                              self.psi[b].data_ptr(), gates.data_ptr(), D, Xs.data_ptr(),
+                                              C.byref(it), C.byref(res), ws.data_ptr(), ws.numel(),
+                                              self._stream()), "osc_pcg_solve")
+                stats[b, 2], stats[b, 3] = float(it.value), float(res.value)
+                if self.Ustar is not None:
+                    self.Ustar[b].copy_(Xs)
+                dh = C.c_double(0.0)
+                _cabi.check(lib.osc_delta_h(C.byref(g), None, C.byref(prm), X.data_ptr(), Xs.data_ptr(),
+                                            gates.data_ptr(), D, C.byref(dh), ws.data_ptr(), ws.numel(),
+                                            self._stream()), "osc_delta_h")
+                out["deltaH"][b] = dh.value
+            out["unresolved"][b] &= 2
+        return len(flagged)
+
+
+def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: int = 6, *,
+                      chunk: int = 512, max_iters: int = 12, tol: float = 1e-3, receipt: bool = True,
+                      out_host: torch.Tensor | None = None, device: torch.device | None = None,
+                      **lattice_kw) -> torch.Tensor:
+    """End-to-end serving call on HOST buffers: for every lattice b of Y_host[B,N,D] (pinned fp32)
+    run ctor + set_query(psi_host[b]) + settle + light receipt (cloud/app/main.py:916-939,1043,1061)
+    and return a pinned [B,5] float64 host tensor {iters, res, ustar_iters, ustar_res, deltaH}.
+
+    The batch is cut into chunks; the H2D copy of chunk i+1 runs on a copy stream while chunk i is
+    built and settled, so PCIe and the SMs work concurrently (two device staging buffers)."""
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    B, N, D = (int(v) for v in Y_host.shape)
+    chunk = max(1, min(int(chunk), B))
+    if out_host is None:
+        out_host = torch.empty((B, 5), dtype=torch.float64, pin_memory=True)
+    res_dev = torch.empty((B, 5), dtype=torch.float64, device=dev)
+    comp = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    bufY = [torch.empty((chunk, N, D), dtype=torch.float32, device=dev) for _ in range(2)]
+    bufP = [torch.empty((chunk, D), dtype=torch.float32, device=dev) for _ in range(2)]
+    copy.wait_stream(comp)
+    free_ev = [None, None]
+    pending = []
+    n_chunks = (B + chunk - 1) // chunk
+    for i in range(n_chunks):
+        lo, hi = i * chunk, min(B, (i + 1) * chunk)
+        s = i & 1
+        with torch.cuda.stream(copy):
+            if free_ev[s] is not None:
+                copy.wait_event(free_ev[s])
+            bufY[s][: hi - lo].copy_(Y_host[lo:hi], non_blocking=True)
+            bufP[s][: hi - lo].copy_(psi_host[lo:hi], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        comp.wait_event(ready)
+        bl = BatchedLattices(bufY[s][: hi - lo], kneighbors=kneighbors, device=dev, **lattice_kw)
+        bl.set_query(bufP[s][: hi - lo])
+        out = bl.settle(max_iters=max_iters, tol=tol, receipt=receipt, strict=False)
+        r = res_dev[lo:hi]
+        r[:, 0], r[:, 1] = out["iters"], out["res"]
+        if receipt:
+            r[:, 2], r[:, 3], r[:, 4] = out["ustar_iters"], out["ustar_res"], out["deltaH"]
+        free_ev[s] = torch.cuda.Event()
+        free_ev[s].record(comp)
+        pending.append((bl, out, lo, hi))
+    out_host.copy_(res_dev, non_blocking=True)
+    comp.synchronize()
+    # flagged lattices (pathological, see BatchedLattices.settle): redo with the global-test PCG.
+    # bufY has been reused by then, so the chunk is fetched again from the host copy.
+    for bl, out, lo, hi in pending:
+        if bool((out["unresolved"] & 1).any()):
+            bl.Y = Y_host[lo:hi].to(dev)
+            bl.psi = psi_host[lo:hi].to(dev)
+            bl.resolve_flagged(out)
+            r = res_dev[lo:hi]
+            r[:, 0], r[:, 1] = out["iters"], out["res"]
+            if receipt:
+                r[:, 2], r[:, 3], r[:, 4] = out["ustar_iters"], out["ustar_res"], out["deltaH"]
+            out_host[lo:hi].copy_(r)
+    return out_host

@@ -1,18 +1,29 @@
 // K3: batched serving kernel -- many small lattices of equal (N, D, k) settled concurrently.
 //
-// Every CG reduction of solver.py:22-36 is per column, so a CTA that owns an 8-column slab of
-// ALL N rows of one lattice can run the whole recurrence on chip:
-//   p (the only vector that is gathered)  -> shared memory  [N][8] fp32
-//   ELL graph (u16 neighbour, fp32 W)     -> shared memory  (re-used by every iteration)
-//   x, r, Ap                              -> registers (each thread owns fixed (row, 4-col) tasks)
-// Only the stop test (max over ALL D columns, solver.py:29-31) crosses CTAs: the G = D/8 CTAs of
-// a lattice form a group that exchanges one float per iteration through global atomics (the
-// grid is launched cooperatively so a group is always co-resident).
+// Every CG reduction of solver.py:22-36 is per column, so a CTA that owns a 4-column slab of ALL
+// N rows of one lattice runs the whole recurrence on chip with no other CTA involved:
+//   p (the only vector that is gathered)  -> shared memory  [N] float4
+//   ELL graph (u16 byte offset, fp32 W)   -> shared memory  (staged once per chunk of slabs)
+//   x, r, Ap                              -> registers (thread owns fixed rows, one float4 each)
 //
-// The same kernel optionally chains: settle (lattice.py:170-207) -> stationary solve
-// (lattice.py:245-265) -> deltaH (receipts.py:21-25), touching HBM only for Y in and U / U* out.
-#include <cooperative_groups.h>
-
+// The one thing that couples the columns of a lattice is the stop test (max over ALL D columns,
+// solver.py:29-31).  It is resolved WITHOUT any cross-CTA synchronisation inside the iteration:
+//   pass 1   every slab iterates until its OWN 4 columns satisfy the test and records
+//            {iterations, max_c ||r_c||^2}.  The lattice's iteration count is T = max over slabs
+//            (the reference stops at the first iteration where every column is below tol).
+//   resolve  slabs that stopped before T are put on a fix list ...
+//   pass 2   ... and re-run for exactly T iterations (same kernel, list mode).  For the usual
+//            case -- all slabs of a lattice need the same count -- the list is empty.
+//   finalize per-lattice {T, res = sqrt(max rr)}, deltaH = sum of slab partials (fixed order), and
+//            an `unresolved` flag for the pathological non-monotone case (a re-run slab is above
+//            tol again at T); the host mirror then settles that lattice with the HBM-resident
+//            PCG (csrc/pcg.cu), which has the global test built in.
+//
+// Because slabs are independent, two CTAs share an SM: while one sits in a reduction/barrier
+// latency chain the other one keeps the shared-memory pipe busy with its gathers.
+//
+// The kernel chains settle (lattice.py:170-207) -> stationary solve (lattice.py:245-265) -> deltaH
+// (receipts.py:21-25), touching HBM only for Y in and U / U* out.
 #include <cstdio>
 #include <cstdlib>
 
@@ -20,42 +31,36 @@
 
 namespace osc {
 
-constexpr int BC = 8;        // columns per slab
-constexpr int BT_MAX = 1024;  // threads per CTA are chosen per shape (multiple of 32)
-constexpr int BW_MAX = BT_MAX / 32;
-#define BT ((int)blockDim.x)
-#define BW ((int)(blockDim.x >> 5))
+constexpr int SC = 4;  // columns per slab (one float4 per row)
+constexpr int PK_MAXK = 16;
+constexpr int RED_F4 = 32;  // float4 slots per reduction array (>= warps per CTA)
 
 struct BatchedK {
-  const int32_t* nbr;
-  const float* W;
-  const int32_t* deg;
   const float* Y;
   const float* U_in;
   const float* psi;
   const float* gates;
   float* U_out;
   float* Ustar_out;
-  float* stats;
-  double* dh_part;
-  unsigned* sync;  // [batch][2 solves][maxit+1]{max bits, arrivals} (zeroed per launch)
-  unsigned long long* prof;  // dev-only phase clocks (block 0, thread 0)
-  const unsigned short* pk_nbr;  // packed graph image [batch][N][kp]
-  const float* pk_w;
-  int64_t batch, N;
-  int k, kp, D, G, groups, maxit;
+  double* dh_part;               // [batch][G]
+  int2* rec;                     // [batch][2][G] {iterations, float bits of max_c ||r_c||^2}
+  const int4* fix_list;          // list mode: {lattice, slab, forced settle its, forced U* its}
+  const int* fix_count;
+  const unsigned short* pk_nbr;  // packed graph image [batch][kq][N] ushort4 (byte offsets j*16)
+  const float* pk_w;             // [batch][kq][N] float4
+  int64_t batch, n_work;
+  int N, kq, D, G, CH, cpl;
   int do_settle, do_ustar, do_dh;
   float lamG, lamC, lamQ, dt;
   double tol_settle, tol_ustar;
   int max_iters_settle, max_iters_ustar;
-  int debug;  // dev-only experiment switches (OSC_BATCHED_DEBUG): 1 = no group wait, 2 = no gathers
 };
 
 struct SolveCoef {
   float diag0, diag1;  // operator diagonal = diag0 + diag1 * b_i
   float offc;
   float lamG, lamQ, dt;
-  int settle, kq, debug;
+  int settle;
 };
 
 __device__ __forceinline__ float md_of(const SolveCoef& c, float b) {
@@ -74,200 +79,103 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
-// sum over all tasks of the CTA that share this thread's column half; one __syncthreads.
-__device__ __forceinline__ float4 block_colsum(float4 v, float4* red, int lane, int warp, int half) {
-#pragma unroll
-  for (int o = 2; o < 32; o <<= 1) {
-    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
-    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
-  }
-  if (lane < 2) red[warp * 2 + lane] = v;
-  __syncthreads();
-  float4 t = f4_zero();
-  const int nw = BW;
-#pragma unroll 4
-  for (int w = 0; w < nw; ++w) t = f4_add(t, red[w * 2 + half]);
+// ---- block reductions of per-column partials ---------------------------------------------------
+// All 32 lanes of a warp hold partials of the SAME 4 columns.  The butterfly halves the number of
+// live values at every step (2 + 1 + 3 = 6 SHFL for 4 values, 4 + 2 + 1 + 2 = 9 for 8), the
+// per-warp totals go to shared memory, and after ONE barrier every thread sums the nw partials
+// itself with broadcast LDS.128 (same order in every thread -> identical, deterministic totals).
+__device__ __forceinline__ void warp_reduce4(float4 v, float4* red_w, int lane) {
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1;
+  const float s0 = b4 ? v.x : v.z, s1 = b4 ? v.y : v.w;
+  float k0 = b4 ? v.z : v.x, k1 = b4 ? v.w : v.y;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const float s = b3 ? k0 : k1;
+  float k = b3 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  if ((lane & 7) == 0) reinterpret_cast<float*>(red_w)[b4 * 2 + b3] = k;  // component b4*2+b3
+}
+__device__ __forceinline__ void warp_reduce8(float4 a, float4 b, float4* red_a, float4* red_b, int lane) {
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+  const float4 s = b4 ? a : b;
+  float4 k = b4 ? b : a;
+  k.x += __shfl_xor_sync(0xffffffffu, s.x, 16);
+  k.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
+  k.z += __shfl_xor_sync(0xffffffffu, s.z, 16);
+  k.w += __shfl_xor_sync(0xffffffffu, s.w, 16);
+  const float s0 = b3 ? k.x : k.z, s1 = b3 ? k.y : k.w;
+  float k0 = b3 ? k.z : k.x, k1 = b3 ? k.w : k.y;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+  const float ss = b2 ? k0 : k1;
+  float kk = b2 ? k1 : k0;
+  kk += __shfl_xor_sync(0xffffffffu, ss, 4);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+  // b4 picks the vector (0: a, 1: b), component = b3*2 + b2
+  if ((lane & 3) == 0) reinterpret_cast<float*>(b4 ? red_b : red_a)[b3 * 2 + b2] = kk;
+}
+__device__ __forceinline__ float4 block_total(const float4* red, int nw) {
+  float4 t = red[0];
+  for (int w = 1; w < nw; ++w) t = f4_add(t, red[w]);
   return t;
 }
-
-#define OSC_TICK(slot)                                                        \
-  do {                                                                        \
-    if (prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {             \
-      const long long _n = clock64();                                         \
-      prof[slot] += (unsigned long long)(_n - tprev);                         \
-      tprev = _n;                                                             \
-    }                                                                         \
-  } while (0)
 
 template <int TPT>
 struct Slab {
   float4 X[TPT], R[TPT], AP[TPT];
 };
 
-// A(p) for one task: diag*p_own - offc * sum_t W_t p[nbr_t]
+// A(p) for one row: diag*p_own - offc * sum_t W_t p[nbr_t]; graph image is slot-major [c][row]
 template <int KQ>
-__device__ __forceinline__ float4 apply_task(const float4* p_s, const ushort4* nbr_s,
-                                             const float4* w_s, int row, int half, int kq_rt,
-                                             float diag, float offc) {
+__device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
+                                            int row, int N, int kq_rt, float diag, float offc) {
   float4 acc = f4_zero();
-  const int kq = (KQ > 0 ? KQ : kq_rt) & 0xff;
-  if (!(kq_rt & 0x200))
+  const int kq = KQ > 0 ? KQ : kq_rt;
+  const char* pb = reinterpret_cast<const char*>(p_s);
 #pragma unroll
   for (int c = 0; c < kq; ++c) {
-    const ushort4 jj = nbr_s[row * kq + c];
-    const float4 ww = w_s[row * kq + c];
-    acc = f4_fma(ww.x, p_s[jj.x * 2 + half], acc);
-    acc = f4_fma(ww.y, p_s[jj.y * 2 + half], acc);
-    acc = f4_fma(ww.z, p_s[jj.z * 2 + half], acc);
-    acc = f4_fma(ww.w, p_s[jj.w * 2 + half], acc);
+    const ushort4 jj = nbr_s[c * N + row];
+    const float4 ww = w_s[c * N + row];
+    acc = f4_fma(ww.x, *reinterpret_cast<const float4*>(pb + jj.x), acc);
+    acc = f4_fma(ww.y, *reinterpret_cast<const float4*>(pb + jj.y), acc);
+    acc = f4_fma(ww.z, *reinterpret_cast<const float4*>(pb + jj.z), acc);
+    acc = f4_fma(ww.w, *reinterpret_cast<const float4*>(pb + jj.w), acc);
   }
-  const float4 own = p_s[row * 2 + half];
+  const float4 own = p_s[row];
   return make_float4(diag * own.x - offc * acc.x, diag * own.y - offc * acc.y,
                      diag * own.z - offc * acc.z, diag * own.w - offc * acc.w);
 }
 
-// sum over lanes of equal parity (lane & 1); every lane ends with its parity's total
-__device__ __forceinline__ float4 warp_parity_sum(float4 v) {
-#pragma unroll
-  for (int o = 2; o < 32; o <<= 1) {
-    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
-    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
-  }
-  return v;
-}
-// second stage, executed redundantly by every warp: totals of the per-warp partials for this
-// lane's parity (all lanes of a parity end with the same value)
-__device__ __forceinline__ float4 warp0_collect(const float4* red, int lane, int nw) {
-  float4 t = f4_zero();
-  for (int w = lane >> 1; w < nw; w += 16) t = f4_add(t, red[w * 2 + (lane & 1)]);
-  return warp_parity_sum(t);
-}
-
-// ---- shuffle-light block reductions ------------------------------------------------------------
-// SHFL issues at ~1 warp-instruction/clk/SM, so reducing 8 separate floats with 4 butterfly steps
-// each (32 SHFL) dominated the update phases.  Here the butterfly halves the number of live
-// values at every step (4+2+1+1 = 8 SHFL for 8 values): after it each lane owns the 16-lane
-// (equal-parity) total of ONE value, which it drops into shared memory.
-__device__ __forceinline__ void reduce4_write(float4 v, float* redw, int lane) {
-  const int b0 = (lane >> 1) & 1, b1 = (lane >> 2) & 1;
-  float s0 = b0 ? v.x : v.z, s1 = b0 ? v.y : v.w;
-  float k0 = b0 ? v.z : v.x, k1 = b0 ? v.w : v.y;
-  k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-  k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-  const float s = b1 ? k0 : k1;
-  float k = b1 ? k1 : k0;
-  k += __shfl_xor_sync(0xffffffffu, s, 4);
-  k += __shfl_xor_sync(0xffffffffu, k, 8);
-  k += __shfl_xor_sync(0xffffffffu, k, 16);
-  if ((lane >> 3) == 0) redw[(lane & 1) * 4 + b0 * 2 + b1] = k;  // value b0*2+b1 of parity lane&1
-}
-// every warp folds the per-warp partials itself; returns the 4 column totals of this lane's parity
-__device__ __forceinline__ float4 collect4(const float* red, float* tscr_w, int lane, int nw) {
-  float t = 0.f;
-  for (int w = lane >> 3; w < nw; w += 4) t += red[w * 8 + (lane & 7)];
-  t += __shfl_xor_sync(0xffffffffu, t, 8);
-  t += __shfl_xor_sync(0xffffffffu, t, 16);
-  if (lane < 8) tscr_w[lane] = t;
-  __syncwarp();
-  const float4 r = *reinterpret_cast<const float4*>(tscr_w + (lane & 1) * 4);
-  __syncwarp();
-  return r;
-}
-__device__ __forceinline__ void reduce8_write(float4 a, float4 b, float* redw, int lane) {
-  const int b0 = (lane >> 1) & 1, b1 = (lane >> 2) & 1, b2 = (lane >> 3) & 1;
-  const float4 s = b0 ? a : b;
-  float4 k = b0 ? b : a;
-  k.x += __shfl_xor_sync(0xffffffffu, s.x, 2);
-  k.y += __shfl_xor_sync(0xffffffffu, s.y, 2);
-  k.z += __shfl_xor_sync(0xffffffffu, s.z, 2);
-  k.w += __shfl_xor_sync(0xffffffffu, s.w, 2);
-  const float s0 = b1 ? k.x : k.z, s1 = b1 ? k.y : k.w;
-  float k0 = b1 ? k.z : k.x, k1 = b1 ? k.w : k.y;
-  k0 += __shfl_xor_sync(0xffffffffu, s0, 4);
-  k1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-  const float ss = b2 ? k0 : k1;
-  float kk = b2 ? k1 : k0;
-  kk += __shfl_xor_sync(0xffffffffu, ss, 8);
-  kk += __shfl_xor_sync(0xffffffffu, kk, 16);
-  if ((lane >> 4) == 0) redw[(lane & 1) * 8 + b0 * 4 + b1 * 2 + b2] = kk;  // value b0*4+b1*2+b2
-}
-__device__ __forceinline__ void collect8(const float* red, float* tscr_w, int lane, int nw, float4& a,
-                                         float4& b) {
-  float t = 0.f;
-  for (int w = lane >> 4; w < nw; w += 2) t += red[w * 16 + (lane & 15)];
-  t += __shfl_xor_sync(0xffffffffu, t, 16);
-  if (lane < 16) tscr_w[lane] = t;
-  __syncwarp();
-  a = *reinterpret_cast<const float4*>(tscr_w + (lane & 1) * 8);
-  b = *reinterpret_cast<const float4*>(tscr_w + (lane & 1) * 8 + 4);
-  __syncwarp();
-}
-
-// ---- group exchange of the per-slab residual maxima -------------------------------------------
-// Per (lattice, solve, iteration): {max bits, arrival count}.  The slab maximum is folded in with
-// a relaxed RED as soon as it is known; the release-add on the counter (which fences) is issued
-// only after the p update, when the first RED has long been acknowledged, so the fence is cheap.
-__device__ __forceinline__ void group_publish_max(unsigned* slot, float mx) {
-  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(slot), "r"(__float_as_uint(fmaxf(mx, 0.f)))
-               : "memory");
-}
-__device__ __forceinline__ void group_publish_arrive(unsigned* slot) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(slot + 1), "r"(1u) : "memory");
-}
-__device__ __forceinline__ unsigned group_wait(unsigned* slot, unsigned G) {
-  unsigned cnt;
-  do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cnt) : "l"(slot + 1) : "memory");
-  } while (cnt < G);
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
-  return v;
-}
-
-// One PCG solve for this CTA's slab (solver.py:15-37).  On exit st.X holds the solution.
-// Returns the iteration count; *res_out is the group-wide max-column residual at that iteration.
-//
-// Reductions: warp shuffle over equal-parity lanes -> per-warp partials in shared memory -> one
-// barrier -> EVERY warp folds the partials itself (2 LDS + 16 SHFL), so no serial section and no
-// second barrier: 3 barriers per iteration.
-//
-// The stop test of iteration `it` needs the maximum over all G slabs of the lattice.  Instead of
-// stalling on it, the CTA publishes its slab maximum, goes straight on to the SpMM of iteration
-// it+1 and only then consumes the group result (prefetched while the SpMM runs): if the solve had
-// converged the speculative SpMM is dropped -- x and r are untouched at that point.
+// One PCG solve for this CTA's slab (solver.py:15-37).  On exit st.X holds the iterate of the
+// returned iteration.  forced == 0: stop at the first iteration whose slab residual is <= tol
+// (or at max_iters); forced > 0: run exactly `forced` iterations.  *rr_out = max_c ||r_c||^2 there.
 template <int TPT, int KQ>
-__device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max_iters, float4* p_s,
-                          const float2* rowc_s, const ushort4* nbr_s, const float4* w_s, float4* red,
-                          unsigned* sync_base, int G, const bool (&act)[TPT], float* res_out,
-                          unsigned* flag_s, unsigned long long* prof) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = tid & 1;
-  const int nw = BW;
-  long long tprev = clock64();
-  float* redf = reinterpret_cast<float*>(red);
-  float* red0 = redf;                 // [BW_MAX][8]   init r.z
-  float* redA = redf + 256;           // [BW_MAX][8]   p.Ap
-  float* redBC = redf + 512;          // [BW_MAX][16]  r.r | r.z'
-  float* tscr = redf + 1024 + warp * 16;
-  const int kqd = c.kq | ((c.debug & 2) << 8);
-  // ---- r0 = b - A x0 ; p = z0 ; rz
-  __syncthreads();  // previous users of p_s / rowc_s are done, rowc_s of this solve is written
+__device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max_iters, int forced,
+                          int N, int kq, float4* p_s, const float2* rowc_s, const ushort4* nbr_s,
+                          const float4* w_s, float4* red, const bool (&act)[TPT], float* rr_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x, nw = T >> 5;
+  float4* redA = red;               // init r.z, then p.Ap
+  float4* redB = red + RED_F4;      // r.r
+  float4* redC = red + 2 * RED_F4;  // r.z'
 #pragma unroll
   for (int m = 0; m < TPT; ++m)
-    if (act[m]) p_s[tid + BT * m] = st.X[m];
-  __syncthreads();
+    if (act[m]) p_s[tid + T * m] = st.X[m];
+  __syncthreads();  // x0 visible; rowc_s of this solve visible
+  // ---- r0 = b - A x0 ; z0 ; rz
   float4 z0[TPT];
   float4 part = f4_zero();
 #pragma unroll
   for (int m = 0; m < TPT; ++m) {
     z0[m] = f4_zero();
     if (act[m]) {
-      const int q = tid + BT * m, row = q >> 1;
+      const int row = tid + T * m;
       const float2 rc = rowc_s[row];
-      const float4 a = apply_task<KQ>(p_s, nbr_s, w_s, row, half, kqd, rc.x, c.offc);
+      const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, rc.x, c.offc);
       float4 r = st.R[m];
       r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
       st.R[m] = r;
@@ -275,53 +183,30 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
       part = f4_add(part, f4_mul(r, z0[m]));
     }
   }
-  reduce4_write(part, red0 + warp * 8, lane);
+  warp_reduce4(part, redA + warp, lane);
   __syncthreads();  // also: every gather of x0 has completed
-  float4 rz = collect4(red0, tscr, lane, nw);
+  float4 rz = block_total(redA, nw);
 #pragma unroll
   for (int m = 0; m < TPT; ++m)
-    if (act[m]) p_s[tid + BT * m] = z0[m];
+    if (act[m]) p_s[tid + T * m] = z0[m];
   __syncthreads();
 
-  OSC_TICK(8);  // init (x0 -> r0, p0)
-  int it = 1, done_it = 0;
-  float res = __int_as_float(0x7fc00000);
+  int it = 1;
+  float mx;
   while (true) {
-    // prefetch the group result of the previous iteration; it lands while the SpMM runs
-    unsigned pre_cnt = 0, pre_val = 0x7f800000u;
-    if (tid == 0 && it > 1 && !(c.debug & 1)) {
-      unsigned* slot = sync_base + 2 * (it - 1);
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(pre_cnt) : "l"(slot + 1) : "memory");
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pre_val) : "l"(slot) : "memory");
-    }
     // ---- A: Ap, p.Ap
     part = f4_zero();
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       if (act[m]) {
-        const int q = tid + BT * m, row = q >> 1;
-        st.AP[m] = apply_task<KQ>(p_s, nbr_s, w_s, row, half, kqd, rowc_s[row].x, c.offc);
-        part = f4_add(part, f4_mul(p_s[q], st.AP[m]));
+        const int row = tid + T * m;
+        st.AP[m] = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, rowc_s[row].x, c.offc);
+        part = f4_add(part, f4_mul(p_s[row], st.AP[m]));
       }
     }
-    OSC_TICK(9);  // A: SpMM
-    reduce4_write(part, redA + warp * 8, lane);
-    if (tid == 0) {
-      unsigned fl = 0x7f800000u;  // +inf: "not converged"
-      if (it > 1 && !(c.debug & 1))
-        fl = (pre_cnt >= (unsigned)G) ? pre_val : group_wait(sync_base + 2 * (it - 1), (unsigned)G);
-      *flag_s = fl;
-    }
+    warp_reduce4(part, redA + warp, lane);
     __syncthreads();
-    if (it > 1) {
-      res = __fsqrt_rn(__uint_as_float(*flag_s));
-      if ((double)res <= tol) {  // solver.py:29-31 -- converged at it-1; drop the speculative Ap
-        done_it = it - 1;
-        break;
-      }
-    }
-    OSC_TICK(10);  // barrier 1 + flag
-    const float4 pap = collect4(redA, tscr, lane, nw);
+    const float4 pap = block_total(redA, nw);
     const float4 alpha = make_float4(__fdiv_rn(rz.x, pap.x + 1e-18f), __fdiv_rn(rz.y, pap.y + 1e-18f),
                                      __fdiv_rn(rz.z, pap.z + 1e-18f), __fdiv_rn(rz.w, pap.w + 1e-18f));
     // ---- C: x, r update; rr and rz'
@@ -331,8 +216,8 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     for (int m = 0; m < TPT; ++m) {
       zz[m] = f4_zero();
       if (act[m]) {
-        const int q = tid + BT * m, row = q >> 1;
-        const float4 p = p_s[q];
+        const int row = tid + T * m;
+        const float4 p = p_s[row];
         float4 x = st.X[m], r = st.R[m];
         const float4 ap = st.AP[m];
         x = make_float4(fmaf(p.x, alpha.x, x.x), fmaf(p.y, alpha.y, x.y), fmaf(p.z, alpha.z, x.z),
@@ -348,27 +233,15 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
         prz = f4_add(prz, f4_mul(r, z));
       }
     }
-    OSC_TICK(11);  // C: update
-    reduce8_write(prr, prz, redBC + warp * 16, lane);
+    warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
     __syncthreads();
-    OSC_TICK(12);  // barrier 2
-    float4 rr, rzn;
-    collect8(redBC, tscr, lane, nw, rr, rzn);
-    if (warp == 0) {  // publish this slab's residual maximum to the group
-      float mx = fmaxf(fmaxf(rr.x, rr.y), fmaxf(rr.z, rr.w));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      if (lane == 0) group_publish_max(sync_base + 2 * it, mx);
-    }
-    if (it == max_iters) {
-      if (tid == 0) {
-        group_publish_arrive(sync_base + 2 * it);
-        *flag_s = (c.debug & 1) ? 0x7f800000u : group_wait(sync_base + 2 * it, (unsigned)G);
-      }
-      __syncthreads();
-      res = __fsqrt_rn(__uint_as_float(*flag_s));
-      done_it = it;
-      break;
-    }
+    const float4 rr = block_total(redB, nw);
+    const float4 rzn = block_total(redC, nw);
+    mx = fmaxf(fmaxf(rr.x, rr.y), fmaxf(rr.z, rr.w));
+    // identical in every thread (same summation order) -> uniform branch
+    const bool stop = forced > 0 ? (it >= forced)
+                                 : ((double)__fsqrt_rn(mx) <= tol || it >= max_iters);
+    if (stop) break;
     // ---- E: p = z + beta p
     const float4 beta = make_float4(__fdiv_rn(rzn.x, rz.x + 1e-18f), __fdiv_rn(rzn.y, rz.y + 1e-18f),
                                     __fdiv_rn(rzn.z, rz.z + 1e-18f), __fdiv_rn(rzn.w, rz.w + 1e-18f));
@@ -376,80 +249,74 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       if (act[m]) {
-        const int q = tid + BT * m;
-        const float4 p = p_s[q];
+        const int row = tid + T * m;
+        const float4 p = p_s[row];
         const float4 z = zz[m];
-        p_s[q] = make_float4(fmaf(p.x, beta.x, z.x), fmaf(p.y, beta.y, z.y), fmaf(p.z, beta.z, z.z),
-                             fmaf(p.w, beta.w, z.w));
+        p_s[row] = make_float4(fmaf(p.x, beta.x, z.x), fmaf(p.y, beta.y, z.y), fmaf(p.z, beta.z, z.z),
+                               fmaf(p.w, beta.w, z.w));
       }
     }
-    if (tid == 0) group_publish_arrive(sync_base + 2 * it);
     __syncthreads();
-    OSC_TICK(13);  // E: p update + barrier 3
     ++it;
   }
-  *res_out = res;
-  return done_it;
+  *rr_out = mx;
+  return it;
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Graph packing pre-pass: ELL (int32 nbr / fp32 W / deg) -> the shared-memory image of the slab
-// kernel ([N][kp] u16 neighbour + [N][kp] fp32 weight, kp = k rounded up to 4).
+// kernel: slot-major [kq][N] ushort4 byte offsets (16*j) + [kq][N] float4 weights, kp = 4*kq.
 //
-// Bank conflicts: a 128-bit shared load is served per quarter-warp = 4 lattice rows (2 lanes per
-// row).  Row j of p occupies banks 8*(j mod 4)..+7, so the 4 rows of a quarter-warp collide
-// whenever two of their t-th neighbours agree mod 4 (2.04 wavefronts per phase for random
-// graphs).  The ORDER in which a row visits its neighbours is free, and padding slots (weight 0)
-// may point at any row, so each group of 4 rows greedily schedules its neighbour lists such that
-// the residues at every step are distinct (measured 1.18 wavefronts per phase).
-constexpr int PK_MAXK = 16;
-
+// Bank conflicts: a 128-bit shared load is served per quarter-warp = 8 consecutive lattice rows.
+// Row j of p occupies banks 4*(j mod 8)..+3, so the 8 rows collide whenever two of their t-th
+// neighbours agree mod 8 (2.5 wavefronts per gather for random graphs).  The ORDER in which a
+// row visits its neighbours is free, and padding slots (weight 0) may point at any row, so each
+// group of 8 rows greedily schedules its neighbour lists such that the residues met at every
+// step are distinct where possible (measured 1.34 wavefronts per gather at N=1200, k=8).
 __global__ void __launch_bounds__(128)
 batched_pack_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ W,
                     const int32_t* __restrict__ deg, int64_t batch, int N, int k, int kp,
                     unsigned short* __restrict__ out_nbr, float* __restrict__ out_w) {
-  const int groups = (N + 3) / 4;
+  const int groups = (N + 7) / 8;
   const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gidx >= batch * groups) return;
   const int64_t b = gidx / groups;
   const int g = (int)(gidx - b * groups);
-  int idx[4][PK_MAXK];
-  float wv[4][PK_MAXK];
-  int cnt[4];
-  unsigned used[4];
+  const int kq = kp / 4;
+  int idx[8][PK_MAXK];
+  int cnt[8], left[8];
+  unsigned used[8];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int row = 4 * g + r;
+  for (int r = 0; r < 8; ++r) {
+    const int row = 8 * g + r;
     cnt[r] = 0;
     used[r] = 0;
     if (row < N) {
       const int d = min(deg[b * N + row], k);
       cnt[r] = d;
-      for (int t = 0; t < d; ++t) {
-        idx[r][t] = nbr[(b * N + row) * k + t];
-        wv[r][t] = W[(b * N + row) * k + t];
-      }
+      for (int t = 0; t < d; ++t) idx[r][t] = nbr[(b * N + row) * k + t];
     }
+    left[r] = cnt[r];
   }
-  int left[4] = {cnt[0], cnt[1], cnt[2], cnt[3]};
   for (int t = 0; t < kp; ++t) {
     unsigned taken = 0;
-    int pick[4] = {-1, -1, -1, -1};
+    int pick[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) pick[r] = -1;
     for (int ps = 0; ps < 2; ++ps) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < 8; ++r) {
         if (pick[r] >= 0 || left[r] == 0) continue;
         const bool must = left[r] >= (kp - t);
         if ((ps == 0) != must) continue;
-        int rc[4] = {0, 0, 0, 0};
+        int rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int e = 0; e < cnt[r]; ++e)
-          if (!((used[r] >> e) & 1u)) rc[idx[r][e] & 3]++;
+          if (!((used[r] >> e) & 1u)) rc[idx[r][e] & 7]++;
         int best = -1, sel = -1, first = -1;
         for (int e = 0; e < cnt[r]; ++e) {
           if ((used[r] >> e) & 1u) continue;
           if (first < 0) first = e;
-          const int res = idx[r][e] & 3;
+          const int res = idx[r][e] & 7;
           if (!((taken >> res) & 1u) && rc[res] > best) {
             best = rc[res];
             sel = e;
@@ -460,351 +327,390 @@ batched_pack_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ W
           pick[r] = sel;
           used[r] |= 1u << sel;
           left[r]--;
-          taken |= 1u << (idx[r][sel] & 3);
+          taken |= 1u << (idx[r][sel] & 7);
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int row = 4 * g + r;
+    for (int r = 0; r < 8; ++r) {
+      const int row = 8 * g + r;
       if (row >= N) continue;
       int j;
       float w;
       if (pick[r] >= 0) {
         j = idx[r][pick[r]];
-        w = wv[r][pick[r]];
+        w = W[(b * N + row) * k + pick[r]];
       } else {
         int res = 0;  // padding: any row whose residue is still free at this step
-        while (res < 3 && ((taken >> res) & 1u)) ++res;
+        while (res < 7 && ((taken >> res) & 1u)) ++res;
         taken |= 1u << res;
         j = res < N ? res : 0;
         w = 0.f;
       }
-      out_nbr[(b * N + row) * kp + t] = (unsigned short)j;
-      out_w[(b * N + row) * kp + t] = w;
+      const int64_t o = ((b * kq + (t >> 2)) * N + row) * 4 + (t & 3);
+      out_nbr[o] = (unsigned short)(j * 16);
+      out_w[o] = w;
     }
   }
 }
 
-template <int TPT, int KQ>
-__global__ void __launch_bounds__(TPT == 3 ? 800 : (TPT == 4 ? 640 : 1024), 1)
-batched_settle_kernel(BatchedK P) {
+template <int TPT, int KQ, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = (int)P.N, kq = P.kp / 4;
-  float4* p_s = reinterpret_cast<float4*>(smem_raw);                 // [N][2]
-  float4* w_s = p_s + (size_t)N * 2;                                  // [N][kq]
-  float4* red = w_s + (size_t)N * kq;                                 // 1536 floats of reduction scratch
-  ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 384);             // [N][kq]
-  float2* rowc_s = reinterpret_cast<float2*>(nbr_s + (size_t)N * kq);  // [N] (diag, 1/Mdiag)
-  float* gates_s = reinterpret_cast<float*>(rowc_s + N);              // [N]
-  unsigned* flag_s = reinterpret_cast<unsigned*>(gates_s + N);
+  const int N = P.N, kq = P.kq;
+  float4* p_s = reinterpret_cast<float4*>(smem_raw);                   // [N]
+  float4* w_s = p_s + N;                                                // [kq][N]
+  float4* red = w_s + (size_t)N * kq;                                   // 3 x RED_F4
+  ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 3 * RED_F4);        // [kq][N]
+  float2* rowc_s = reinterpret_cast<float2*>(nbr_s + (size_t)N * kq);   // [N] (diag, 1/Mdiag)
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = tid & 1;
-  const int gid = blockIdx.x / P.G, slab = blockIdx.x % P.G;
-  const int col = slab * BC + half * 4;
-  const bool col_ok = col + 3 < P.D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x;
   bool act[TPT];
 #pragma unroll
-  for (int m = 0; m < TPT; ++m) act[m] = col_ok && ((tid + BT * m) >> 1) < N;
+  for (int m = 0; m < TPT; ++m) act[m] = (tid + T * m) < N;
 
-  unsigned long long* prof = P.prof;
-  long long tprev = clock64();
-  for (int64_t b = gid; b < P.batch; b += P.groups) {
-    __syncthreads();
-    OSC_TICK(0);  // loop top barrier
-    // ---- stage the packed graph image + gates (straight 16 B copies)
+  const bool list_mode = P.fix_list != nullptr;
+  const int64_t n_work = list_mode ? (int64_t)(*P.fix_count) : P.n_work;
+  for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    int64_t b;
+    int s0, s1, Fs = 0, Fu = 0;
+    if (list_mode) {
+      const int4 e = P.fix_list[wk];
+      b = e.x;
+      s0 = e.y;
+      s1 = s0 + 1;
+      Fs = e.z;
+      Fu = e.w;
+    } else {
+      b = wk / P.cpl;
+      s0 = (int)(wk - b * P.cpl) * P.CH;
+      s1 = min(s0 + P.CH, P.G);
+    }
+    __syncthreads();  // readers of the previous graph image are done
     {
-      const uint4* src_w = reinterpret_cast<const uint4*>(P.pk_w + b * P.N * P.kp);
+      const uint4* src_w = reinterpret_cast<const uint4*>(P.pk_w) + b * N * kq;
       uint4* dst_w = reinterpret_cast<uint4*>(w_s);
-      for (int e = tid; e < N * kq; e += BT) dst_w[e] = src_w[e];
-      const uint2* src_n = reinterpret_cast<const uint2*>(P.pk_nbr + b * P.N * P.kp);
+      for (int e = tid; e < N * kq; e += T) dst_w[e] = __ldg(src_w + e);
+      const uint2* src_n = reinterpret_cast<const uint2*>(P.pk_nbr) + b * N * kq;
       uint2* dst_n = reinterpret_cast<uint2*>(nbr_s);
-      for (int e = tid; e < N * kq; e += BT) dst_n[e] = src_n[e];
-      for (int e = tid; e < N; e += BT) gates_s[e] = P.gates ? P.gates[b * P.N + e] : 1.0f;
+      for (int e = tid; e < N * kq; e += T) dst_n[e] = __ldg(src_n + e);
     }
-    const float* Yb = P.Y + b * P.N * P.D;
-    const float* Ub = (P.U_in ? P.U_in : P.Y) + b * P.N * P.D;
-    float* Uo = P.U_out ? P.U_out + b * P.N * P.D : nullptr;
-    const float4 psi4 = col_ok ? *reinterpret_cast<const float4*>(P.psi + b * P.D + col) : f4_zero();
-    __syncthreads();
+    const float* Yb = P.Y + b * (int64_t)N * P.D;
+    const float* Ub = (P.U_in ? P.U_in : P.Y) + b * (int64_t)N * P.D;
+    float* Uo = P.U_out ? P.U_out + b * (int64_t)N * P.D : nullptr;
+    const float* gb = P.gates ? P.gates + b * N : nullptr;
 
-    OSC_TICK(1);  // graph staging
-    Slab<TPT> st;
-    unsigned* sync_b = P.sync + (size_t)b * 2 * (P.maxit + 1) * 2;
-    float res = 0.f;
-    int iters = 0;
-    // ---------------- settle: (I + dt M) U+ = U + dt (lamG Y + lamQ b psi^T), x0 = U
-    if (P.do_settle) {
-      SolveCoef c;
-      c.lamG = P.lamG; c.lamQ = P.lamQ; c.dt = P.dt;
-      c.settle = 1;
-      c.kq = kq;
-      c.debug = P.debug;
-      c.diag0 = 1.0f + P.dt * (P.lamG + P.lamC);
-      c.diag1 = P.dt * P.lamQ;
-      c.offc = P.dt * P.lamC;
-#pragma unroll
-      for (int m = 0; m < TPT; ++m) {
-        st.X[m] = st.R[m] = st.AP[m] = f4_zero();
-        if (act[m]) {
-          const int row = (tid + BT * m) >> 1;
-          const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
-          const float4 u = P.U_in ? *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col) : y;
-          const float bq = gates_s[row];
-          const float4 rhs = make_float4(
-              __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
-              __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
-              __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.z))),
-              __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
-          st.X[m] = u;
-          st.R[m] = make_float4(__fadd_rn(u.x, __fmul_rn(P.dt, rhs.x)), __fadd_rn(u.y, __fmul_rn(P.dt, rhs.y)),
-                                __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w)));
+    for (int s = s0; s < s1; ++s) {
+      const int col = s * SC;
+      const float4 psi4 = *reinterpret_cast<const float4*>(P.psi + b * P.D + col);
+      Slab<TPT> st;
+      float rr = 0.f;
+      // ---------------- settle: (I + dt M) U+ = U + dt (lamG Y + lamQ b psi^T), x0 = U
+      if (P.do_settle) {
+        SolveCoef c;
+        c.lamG = P.lamG; c.lamQ = P.lamQ; c.dt = P.dt;
+        c.settle = 1;
+        c.diag0 = 1.0f + P.dt * (P.lamG + P.lamC);
+        c.diag1 = P.dt * P.lamQ;
+        c.offc = P.dt * P.lamC;
+        __syncthreads();  // previous solve's readers of rowc_s / p_s are done
+        for (int e = tid; e < N; e += T) {
+          const float bq = gb ? gb[e] : 1.0f;
+          rowc_s[e] = make_float2(c.diag0 + c.diag1 * bq, __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f));
         }
-      }
-      for (int e = tid; e < N; e += BT) {
-        const float bq = gates_s[e];
-        rowc_s[e] = make_float2(c.diag0 + c.diag1 * bq, __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f));
-      }
-      OSC_TICK(2);  // settle: load Y/U, rhs
-      iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, p_s, rowc_s, nbr_s, w_s, red,
-                                  sync_b, P.G, act, &res, flag_s, prof);
-      tprev = clock64();
-      if (Uo != nullptr) {
-#pragma unroll
-        for (int m = 0; m < TPT; ++m)
-          if (act[m])
-            *reinterpret_cast<float4*>(Uo + (int64_t)((tid + BT * m) >> 1) * P.D + col) = st.X[m];
-      }
-      if (slab == 0 && tid == 0 && P.stats) {
-        P.stats[b * 4 + 0] = (float)iters;
-        P.stats[b * 4 + 1] = res;
-      }
-    }
-    // ---------------- stationary: M U* = lamG Y + lamQ b psi^T, x0 = Y
-    if (P.do_ustar) {
-      SolveCoef c;
-      c.lamG = P.lamG; c.lamQ = P.lamQ; c.dt = 0.f;
-      c.settle = 0;
-      c.kq = kq;
-      c.debug = P.debug;
-      c.diag0 = P.lamG + P.lamC;
-      c.diag1 = P.lamQ;
-      c.offc = P.lamC;
-#pragma unroll
-      for (int m = 0; m < TPT; ++m) {
-        st.X[m] = st.R[m] = st.AP[m] = f4_zero();
-        if (act[m]) {
-          const int row = (tid + BT * m) >> 1;
-          const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
-          const float bq = gates_s[row];
-          st.X[m] = y;
-          st.R[m] = make_float4(
-              __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
-              __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
-              __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.z))),
-              __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
-        }
-      }
-      OSC_TICK(3);  // store U, load Y, rhs (stationary)
-      __syncthreads();  // the settle solve's readers of rowc_s are done
-      for (int e = tid; e < N; e += BT) {
-        const float bq = gates_s[e];
-        rowc_s[e] = make_float2(c.diag0 + c.diag1 * bq, __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f));
-      }
-      iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, p_s, rowc_s, nbr_s, w_s, red,
-                                  sync_b + (P.maxit + 1) * 2, P.G, act, &res, flag_s, prof);
-      tprev = clock64();
-      if (P.Ustar_out != nullptr) {
-        float* So = P.Ustar_out + b * P.N * P.D;
-#pragma unroll
-        for (int m = 0; m < TPT; ++m)
-          if (act[m])
-            *reinterpret_cast<float4*>(So + (int64_t)((tid + BT * m) >> 1) * P.D + col) = st.X[m];
-      }
-      if (slab == 0 && tid == 0 && P.stats) {
-        P.stats[b * 4 + 2] = (float)iters;
-        P.stats[b * 4 + 3] = res;
-      }
-      // ---------------- deltaH = <U - U*, M (U - U*)>
-      if (P.do_dh) {
-        __syncthreads();
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
+          st.X[m] = st.R[m] = st.AP[m] = f4_zero();
           if (act[m]) {
-            // the settled state: just written by this very thread (U_out) or the caller's U
-            const float* usrc = P.do_settle ? Uo : Ub;
-            const float4 u = *reinterpret_cast<const float4*>(usrc + (int64_t)((tid + BT * m) >> 1) * P.D + col);
-            const float4 s = st.X[m];
-            p_s[tid + BT * m] = make_float4(__fsub_rn(u.x, s.x), __fsub_rn(u.y, s.y),
-                                            __fsub_rn(u.z, s.z), __fsub_rn(u.w, s.w));
+            const int row = tid + T * m;
+            const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
+            const float4 u = P.U_in ? *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col) : y;
+            const float bq = gb ? gb[row] : 1.0f;
+            const float4 rhs = make_float4(
+                __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
+                __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
+                __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.z))),
+                __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
+            st.X[m] = u;
+            st.R[m] = make_float4(__fadd_rn(u.x, __fmul_rn(P.dt, rhs.x)), __fadd_rn(u.y, __fmul_rn(P.dt, rhs.y)),
+                                  __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w)));
           }
         }
-        __syncthreads();
-        float4 part = f4_zero();
+        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, N, kq, p_s,
+                                              rowc_s, nbr_s, w_s, red, act, &rr);
+        if (Uo != nullptr) {
+#pragma unroll
+          for (int m = 0; m < TPT; ++m)
+            if (act[m]) *reinterpret_cast<float4*>(Uo + (int64_t)(tid + T * m) * P.D + col) = st.X[m];
+        }
+        if (tid == 0) P.rec[(b * 2 + 0) * P.G + s] = make_int2(iters, __float_as_int(rr));
+      }
+      // ---------------- stationary: M U* = lamG Y + lamQ b psi^T, x0 = Y
+      if (P.do_ustar) {
+        SolveCoef c;
+        c.lamG = P.lamG; c.lamQ = P.lamQ; c.dt = 0.f;
+        c.settle = 0;
+        c.diag0 = P.lamG + P.lamC;
+        c.diag1 = P.lamQ;
+        c.offc = P.lamC;
+        __syncthreads();  // the settle solve's readers of rowc_s are done
+        for (int e = tid; e < N; e += T) {
+          const float bq = gb ? gb[e] : 1.0f;
+          rowc_s[e] = make_float2(c.diag0 + c.diag1 * bq, __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f));
+        }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
+          st.X[m] = st.R[m] = st.AP[m] = f4_zero();
           if (act[m]) {
-            const int q = tid + BT * m, row = q >> 1;
-            const float4 a = apply_task<KQ>(p_s, nbr_s, w_s, row, half, kq, rowc_s[row].x, c.offc);
-            part = f4_add(part, f4_mul(p_s[q], a));
+            const int row = tid + T * m;
+            const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
+            const float bq = gb ? gb[row] : 1.0f;
+            st.X[m] = y;
+            st.R[m] = make_float4(
+                __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
+                __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
+                __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.z))),
+                __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
           }
         }
-        const float4 tot = block_colsum(part, red, lane, warp, half);
-        float s4 = (tot.x + tot.y) + (tot.z + tot.w);
-        s4 += __shfl_xor_sync(0xffffffffu, s4, 1);
-        if (tid == 0) P.dh_part[b * P.G + slab] = (double)s4;
+        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, N, kq, p_s,
+                                              rowc_s, nbr_s, w_s, red, act, &rr);
+        if (P.Ustar_out != nullptr) {
+          float* So = P.Ustar_out + b * (int64_t)N * P.D;
+#pragma unroll
+          for (int m = 0; m < TPT; ++m)
+            if (act[m]) *reinterpret_cast<float4*>(So + (int64_t)(tid + T * m) * P.D + col) = st.X[m];
+        }
+        if (tid == 0) P.rec[(b * 2 + 1) * P.G + s] = make_int2(iters, __float_as_int(rr));
+        // ---------------- deltaH = <U - U*, M (U - U*)>
+        if (P.do_dh) {
+#pragma unroll
+          for (int m = 0; m < TPT; ++m) {
+            if (act[m]) {
+              const int row = tid + T * m;
+              // the settled state: written by this very thread a moment ago (U_out), or the caller's U
+              const float* usrc = P.do_settle ? Uo : Ub;
+              const float4 u = *reinterpret_cast<const float4*>(usrc + (int64_t)row * P.D + col);
+              const float4 x = st.X[m];
+              p_s[row] = make_float4(__fsub_rn(u.x, x.x), __fsub_rn(u.y, x.y), __fsub_rn(u.z, x.z),
+                                     __fsub_rn(u.w, x.w));
+            }
+          }
+          __syncthreads();
+          float4 part = f4_zero();
+#pragma unroll
+          for (int m = 0; m < TPT; ++m) {
+            if (act[m]) {
+              const int row = tid + T * m;
+              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, rowc_s[row].x, c.offc);
+              part = f4_add(part, f4_mul(p_s[row], a));
+            }
+          }
+          warp_reduce4(part, red + warp, lane);
+          __syncthreads();
+          if (tid == 0) {
+            const float4 tot = block_total(red, T >> 5);
+            P.dh_part[b * P.G + s] = (double)((tot.x + tot.y) + (tot.z + tot.w));
+          }
+        }
       }
-      OSC_TICK(4);  // store U*, deltaH
     }
   }
 }
 
-__global__ void batched_dh_reduce_kernel(const double* __restrict__ part, int G, int64_t batch,
-                                         double* __restrict__ out) {
+// slabs whose own stop came before the lattice-wide count T = max over slabs go on the fix list
+__global__ void batched_resolve_kernel(const int2* __restrict__ rec, int64_t batch, int G, int do_settle,
+                                       int do_ustar, int4* __restrict__ list, int* __restrict__ count,
+                                       int32_t* __restrict__ flags) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  double s = 0.0;
-  for (int g = 0; g < G; ++g) s += part[b * G + g];
-  out[b] = s;
+  int Ts = 0, Tu = 0;
+  for (int s = 0; s < G; ++s) {
+    if (do_settle) Ts = max(Ts, rec[(b * 2 + 0) * G + s].x);
+    if (do_ustar) Tu = max(Tu, rec[(b * 2 + 1) * G + s].x);
+  }
+  int any = 0;
+  for (int s = 0; s < G; ++s) {
+    const bool bad = (do_settle && rec[(b * 2 + 0) * G + s].x != Ts) ||
+                     (do_ustar && rec[(b * 2 + 1) * G + s].x != Tu);
+    if (bad) {
+      list[atomicAdd(count, 1)] = make_int4((int)b, s, Ts, Tu);
+      any = 2;
+    }
+  }
+  if (flags) flags[b] = any;  // bit 1: some slab of this lattice is re-run in pass 2
+}
+
+__global__ void batched_finalize_kernel(const int2* __restrict__ rec, const double* __restrict__ dh_part,
+                                        int64_t batch, int G, int do_settle, int do_ustar, int do_dh,
+                                        double tol_s, double tol_u, int max_s, int max_u,
+                                        float* __restrict__ stats, double* __restrict__ deltaH,
+                                        int32_t* __restrict__ unresolved, int force_bad) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  int bad = force_bad;
+  for (int sv = 0; sv < 2; ++sv) {
+    if (!(sv == 0 ? do_settle : do_ustar)) continue;
+    int T = 0, Tmin = 0x7fffffff;
+    float rr = 0.f;
+    for (int s = 0; s < G; ++s) {
+      const int2 e = rec[(b * 2 + sv) * G + s];
+      T = max(T, e.x);
+      Tmin = min(Tmin, e.x);
+      rr = fmaxf(rr, __int_as_float(e.y));
+    }
+    const float res = __fsqrt_rn(rr);
+    // after the fix pass every slab sits at T; a re-run slab above tol at T < max_iters means the
+    // residual was not monotone there and the true stop is later -> host falls back for this lattice
+    if (Tmin != T) bad = 1;
+    if (T < (sv == 0 ? max_s : max_u) && !((double)res <= (sv == 0 ? tol_s : tol_u))) bad = 1;
+    if (stats) {
+      stats[b * 4 + 2 * sv] = (float)T;
+      stats[b * 4 + 2 * sv + 1] = res;
+    }
+  }
+  if (do_dh) {
+    double s = 0.0;
+    for (int g = 0; g < G; ++g) s += dh_part[b * G + g];
+    deltaH[b] = s;
+  }
+  if (unresolved) unresolved[b] = (unresolved[b] & 2) | bad;  // bit 0: host must fall back
 }
 
 // ================================================================= host side
-// tasks per thread / threads per CTA: 2N float4 tasks spread over at most 1024 threads, keeping
-// x, r, Ap (12 registers per task) inside the per-thread register budget
-static int tpt_for(int64_t N) {
-  const int64_t tasks = 2 * N;
-  if (tasks <= 1024) return 1;
-  if (tasks <= 2 * 1024) return 2;
-  if (tasks <= 3 * 800) return 3;
-  if (tasks <= 4 * 640) return 4;
-  return 0;
-}
+static int tpt_for(int64_t N) { return N <= 320 ? 1 : (N <= 640 ? 2 : 4); }
 static int threads_for(int64_t N, int tpt) {
-  int t = (int)((2 * N + tpt - 1) / tpt);
+  int t = (int)((N + tpt - 1) / tpt);
   t = (t + 31) / 32 * 32;
-  return t < 64 ? 64 : t;
+  return t < 32 ? 32 : t;
 }
-
 static size_t batched_smem(int64_t N, int k) {
   const int kp = (k + 3) / 4 * 4;
-  return (size_t)N * 32 + (size_t)N * kp * 4 + (size_t)N * kp * 2 + 384 * 16 + (size_t)N * 12 +
-         16;
+  return (size_t)N * 16 + (size_t)N * kp * 4 + 3 * RED_F4 * 16 + (size_t)N * kp * 2 + (size_t)N * 8;
 }
 
 int batched_supported(int64_t N, int D, int k) {
-  if (N < 1 || N > 65535 || tpt_for(N) == 0) return 0;
+  if (N < 1 || N > 2560) return 0;
   if (D % 4 != 0 || D < 4) return 0;
-  const int G = (D + BC - 1) / BC;
-  if (G > sm_count()) return 0;
-  if (k < 1 || k > 16 || batched_smem(N, k) > 227 * 1024) return 0;
+  if (k < 1 || k > PK_MAXK || batched_smem(N, k) > 227 * 1024) return 0;
   return 1;
 }
 
 int batched_workspace(int64_t batch, int64_t N, int D, size_t* bytes) {
-  const int G = (D + BC - 1) / BC;
-  const int maxit = 256;
-  *bytes = align_up((size_t)batch * 2 * (maxit + 1) * 2 * sizeof(unsigned)) +
-           align_up((size_t)batch * G * sizeof(double)) + 2048 +
-           align_up((size_t)batch * N * 16 * sizeof(unsigned short)) +
-           align_up((size_t)batch * N * 16 * sizeof(float));
+  const int G = D / SC;
+  *bytes = align_up((size_t)batch * 2 * G * sizeof(int2)) + align_up((size_t)batch * G * sizeof(double)) +
+           align_up((size_t)batch * G * sizeof(int4)) + align_up(sizeof(int)) +
+           align_up((size_t)batch * N * PK_MAXK * sizeof(unsigned short)) +
+           align_up((size_t)batch * N * PK_MAXK * sizeof(float)) + 1024;
   return OSC_OK;
+}
+
+typedef void (*BatchedFn)(BatchedK);
+template <int TPT, int MAXT, int MINB>
+static BatchedFn pick_kq(int kq) {
+  switch (kq) {
+    case 1: return batched_settle_kernel<TPT, 1, MAXT, MINB>;
+    case 2: return batched_settle_kernel<TPT, 2, MAXT, MINB>;
+    case 3: return batched_settle_kernel<TPT, 3, MAXT, MINB>;
+    default: return batched_settle_kernel<TPT, 4, MAXT, MINB>;
+  }
 }
 
 int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batched_args_t* a,
                    void* workspace, size_t ws_bytes, cudaStream_t st) {
   OSC_REQUIRE(g != nullptr && prm != nullptr && a != nullptr, "batched_settle: NULL argument");
   if (!batched_supported(g->N, a->D, g->k))
-    return fail(OSC_ERR_UNSUPPORTED, "batched_settle: shape not covered (need N<=1280, D%4==0, D<=8*SMs)");
+    return fail(OSC_ERR_UNSUPPORTED, "batched_settle: shape not covered (need N<=2560, D%4==0, k<=16)");
   if (prm->chain_present) return fail(OSC_ERR_UNSUPPORTED, "batched_settle: chain prior not supported");
   OSC_REQUIRE(a->Y != nullptr && a->psi != nullptr, "batched_settle: Y/psi NULL");
+  OSC_REQUIRE(a->do_settle || a->do_ustar, "batched_settle: nothing to do");
   OSC_REQUIRE(!a->do_deltaH || (a->do_ustar && a->deltaH != nullptr), "deltaH needs do_ustar");
   OSC_REQUIRE(!(a->do_settle && a->do_deltaH) || a->U_out != nullptr, "deltaH after settle needs U_out");
-  const int maxit = a->max_iters_settle > a->max_iters_ustar ? a->max_iters_settle : a->max_iters_ustar;
-  OSC_REQUIRE(maxit >= 1 && maxit <= 256, "batched_settle: max_iters must be in [1,256]");
+  OSC_REQUIRE(!a->do_settle || (a->max_iters_settle >= 1 && a->max_iters_settle <= 65535),
+              "batched_settle: max_iters must be in [1,65535]");
+  OSC_REQUIRE(!a->do_ustar || (a->max_iters_ustar >= 1 && a->max_iters_ustar <= 65535),
+              "batched_settle: max_iters must be in [1,65535]");
   if (g->batch == 0) return OSC_OK;
   size_t need = 0;
   batched_workspace(g->batch, g->N, a->D, &need);
   if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "batched_settle: workspace too small");
 
+  const int N = (int)g->N, kp = (g->k + 3) / 4 * 4, kq = kp / 4, G = a->D / SC;
+  Arena ar(workspace, ws_bytes);
+  int2* rec = ar.take<int2>((size_t)g->batch * 2 * G);
+  double* dh_part = ar.take<double>((size_t)g->batch * G);
+  int4* fix_list = ar.take<int4>((size_t)g->batch * G);
+  int* fix_count = ar.take<int>(1);
+  unsigned short* pn = ar.take<unsigned short>((size_t)g->batch * N * kp);
+  float* pw = ar.take<float>((size_t)g->batch * N * kp);
+  if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "batched_settle: workspace too small");
+  OSC_CUDA(cudaMemsetAsync(fix_count, 0, sizeof(int), st));
+  {
+    const int64_t groups8 = g->batch * ((N + 7) / 8);
+    batched_pack_kernel<<<(unsigned)((groups8 + 127) / 128), 128, 0, st>>>(g->nbr, g->W, g->deg, g->batch, N,
+                                                                           g->k, kp, pn, pw);
+    OSC_LAUNCH_CHECK("batched_pack_kernel");
+  }
+
   BatchedK P;
-  P.nbr = g->nbr; P.W = g->W; P.deg = g->deg;
   P.Y = a->Y; P.U_in = a->U_in; P.psi = a->psi; P.gates = a->gates;
-  P.U_out = a->U_out; P.Ustar_out = a->Ustar_out; P.stats = a->stats;
-  P.batch = g->batch; P.N = g->N; P.k = g->k; P.kp = (g->k + 3) / 4 * 4; P.D = a->D;
-  P.G = (a->D + BC - 1) / BC;
-  int groups = sm_count() / P.G;
-  if ((int64_t)groups > g->batch) groups = (int)g->batch;
-  P.groups = groups;
-  P.maxit = 256;
+  P.U_out = a->U_out; P.Ustar_out = a->Ustar_out;
+  P.dh_part = dh_part; P.rec = rec;
+  P.fix_list = nullptr; P.fix_count = nullptr;
+  P.pk_nbr = pn; P.pk_w = pw;
+  P.batch = g->batch; P.N = N; P.kq = kq; P.D = a->D; P.G = G;
+  P.CH = 2;
+  {
+    const char* e = getenv("OSC_BATCHED_CHUNK");  // dev-only: slabs per staged graph image
+    if (e && atoi(e) >= 1) P.CH = atoi(e);
+  }
+  if (P.CH > G) P.CH = G;
+  P.cpl = (G + P.CH - 1) / P.CH;
+  P.n_work = g->batch * P.cpl;
   P.do_settle = a->do_settle; P.do_ustar = a->do_ustar; P.do_dh = a->do_deltaH;
   P.lamG = prm->lamG; P.lamC = prm->lamC; P.lamQ = prm->lamQ; P.dt = a->dt;
   P.tol_settle = a->tol_settle; P.tol_ustar = a->tol_ustar;
   P.max_iters_settle = a->max_iters_settle; P.max_iters_ustar = a->max_iters_ustar;
-  {
-    const char* dbg = getenv("OSC_BATCHED_DEBUG");
-    P.debug = dbg ? atoi(dbg) : 0;
-  }
-  Arena ar(workspace, ws_bytes);
-  const size_t sync_n = (size_t)g->batch * 2 * (P.maxit + 1) * 2;
-  P.sync = ar.take<unsigned>(sync_n);
-  P.dh_part = ar.take<double>((size_t)g->batch * P.G);
-  if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "batched_settle: workspace too small");
-  OSC_CUDA(cudaMemsetAsync(P.sync, 0, sync_n * sizeof(unsigned), st));
-  {
-    unsigned short* pn = ar.take<unsigned short>((size_t)g->batch * g->N * P.kp);
-    float* pw = ar.take<float>((size_t)g->batch * g->N * P.kp);
-    if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "batched_settle: workspace too small");
-    const int64_t groups4 = g->batch * ((g->N + 3) / 4);
-    batched_pack_kernel<<<(unsigned)((groups4 + 127) / 128), 128, 0, st>>>(g->nbr, g->W, g->deg, g->batch,
-                                                                           (int)g->N, g->k, P.kp, pn, pw);
-    OSC_LAUNCH_CHECK("batched_pack_kernel");
-    P.pk_nbr = pn;
-    P.pk_w = pw;
-  }
-  P.prof = nullptr;
-  if (P.debug & 16) {
-    P.prof = ar.take<unsigned long long>(16);
-    if (P.prof) OSC_CUDA(cudaMemsetAsync(P.prof, 0, 16 * sizeof(unsigned long long), st));
-  }
 
-  const size_t smem = batched_smem(g->N, g->k);
-  int tpt = tpt_for(g->N);
+  const size_t smem = batched_smem(N, g->k);
+  const int tpt = tpt_for(N);
+  const int threads = threads_for(N, tpt);
+  BatchedFn fn;
+  if (tpt == 1) fn = pick_kq<1, 320, 2>(kq);
+  else if (tpt == 2) fn = pick_kq<2, 320, 2>(kq);
+  else if (threads <= 320) fn = pick_kq<4, 320, 2>(kq);
+  else fn = pick_kq<4, 640, 1>(kq);
+  OSC_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, threads, smem));
+  if (occ < 1) return fail(OSC_ERR_UNSUPPORTED, "batched_settle: kernel does not fit on an SM");
+  const int64_t resident = (int64_t)occ * sm_count();
+  const unsigned grid = (unsigned)(P.n_work < resident ? P.n_work : resident);
+  fn<<<grid, threads, smem, st>>>(P);
+  OSC_LAUNCH_CHECK("batched_settle_kernel");
+
+  batched_resolve_kernel<<<(unsigned)((g->batch + 127) / 128), 128, 0, st>>>(
+      rec, g->batch, G, a->do_settle, a->do_ustar, fix_list, fix_count, a->unresolved);
+  OSC_LAUNCH_CHECK("batched_resolve_kernel");
   {
-    const char* t = getenv("OSC_BATCHED_TPT");  // dev-only override
-    if (t && atoi(t) >= tpt && atoi(t) <= 4) tpt = atoi(t);
+    BatchedK Q = P;
+    Q.fix_list = fix_list;
+    Q.fix_count = fix_count;
+    const int64_t worst = g->batch * G;
+    const unsigned grid2 = (unsigned)(worst < resident ? worst : resident);
+    fn<<<grid2, threads, smem, st>>>(Q);
+    OSC_LAUNCH_CHECK("batched_settle_kernel(fix)");
   }
-  const int kq = P.kp / 4;
-  void* args[] = {&P};
-  const dim3 grid(groups * P.G), block(threads_for(g->N, tpt));
-  const void* fn = nullptr;
-#define OSC_PICK(T)                                                         \
-  (kq == 1 ? (const void*)batched_settle_kernel<T, 1>                        \
-           : kq == 2 ? (const void*)batched_settle_kernel<T, 2>              \
-                     : kq == 4 ? (const void*)batched_settle_kernel<T, 4>    \
-                               : (const void*)batched_settle_kernel<T, 0>)
-  if (tpt == 1) fn = OSC_PICK(1);
-  else if (tpt == 2) fn = OSC_PICK(2);
-  else if (tpt == 3) fn = OSC_PICK(3);
-  else fn = OSC_PICK(4);
-#undef OSC_PICK
-  OSC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OSC_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st));
-  if (P.prof != nullptr) {
-    unsigned long long h[16];
-    OSC_CUDA(cudaMemcpyAsync(h, P.prof, sizeof(h), cudaMemcpyDeviceToHost, st));
-    OSC_CUDA(cudaStreamSynchronize(st));
-    const char* names[16] = {"top", "stage", "load_settle", "store_load", "store_dh", "", "", "", "init", "A_spmm",
-                             "bar1", "C_update", "bar2", "E_pupd", "", ""};
-    unsigned long long tot = 0;
-    for (int i = 0; i < 16; ++i) tot += h[i];
-    for (int i = 0; i < 16; ++i)
-      if (h[i]) fprintf(stderr, "[osc prof] %-12s %12llu clk %5.1f%%\n", names[i], h[i], 100.0 * h[i] / tot);
+  int force_bad = 0;
+  {
+    const char* e = getenv("OSC_BATCHED_FORCE_UNRESOLVED");  // test hook for the host fallback path
+    if (e && atoi(e) != 0) force_bad = 1;
   }
-  if (a->do_deltaH) {
-    batched_dh_reduce_kernel<<<(unsigned)((g->batch + 127) / 128), 128, 0, st>>>(P.dh_part, P.G,
-                                                                                  g->batch, a->deltaH);
-    OSC_LAUNCH_CHECK("batched_dh_reduce_kernel");
-  }
+  batched_finalize_kernel<<<(unsigned)((g->batch + 127) / 128), 128, 0, st>>>(
+      rec, dh_part, g->batch, G, a->do_settle, a->do_ustar, a->do_deltaH, a->tol_settle, a->tol_ustar,
+      a->max_iters_settle, a->max_iters_ustar, a->stats, a->deltaH, a->unresolved, force_bad);
+  OSC_LAUNCH_CHECK("batched_finalize_kernel");
   return OSC_OK;
 }
 

@@ -90,3 +90,85 @@ def test_batched_with_gates_and_second_settle():
         assert np.linalg.norm(U[b] - o.U) / np.linalg.norm(o.U) < TOL
         ous, _, _ = o.stationary()
         assert rel(float(out["deltaH"][b].item()), o.delta_h(ous)) < 1e-4
+
+
+def _uneven_inputs(B, N, D, seed0=70):
+    """Columns 0-7 carry almost no signal, so their slabs satisfy the stop test iterations before
+    the rest of the lattice does: exercises the resolve + re-run pass of the slab kernel."""
+    Y, _ = _inputs(B, N, D, seed0)
+    Y[:, :, :8] *= 1e-4
+    psi = np.zeros((B, D), dtype=np.float32)
+    psi[:, 8:] = Y[:, :16, 8:].mean(axis=1)
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True) + 1e-12
+    return Y, psi.astype(np.float32)
+
+
+def test_batched_uneven_slabs_are_rerun_to_lattice_count():
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    B, N, D, k = 3, 320, 48, 6
+    Y, psi = _uneven_inputs(B, N, D)
+    bl = BatchedLattices(Y, kneighbors=k)
+    bl.set_query(psi)
+    out = bl.settle(max_iters=12, tol=1e-3, receipt=True, keep_ustar=True)
+    torch.cuda.synchronize()
+    flags = out["unresolved"].cpu().numpy()
+    assert (flags & 2).all(), "expected the early slabs to be re-run"
+    assert not (flags & 1).any()
+    U, Us = bl.U.cpu().numpy(), bl.Ustar.cpu().numpy()
+    for b in range(B):
+        o = SparseLattice(Y[b], k=k)
+        o.set_query(psi[b])
+        st = o.settle(max_iters=12, tol=1e-3)
+        ous, it, res = o.stationary()
+        assert int(out["iters"][b].item()) == st["iters"]
+        assert int(out["ustar_iters"][b].item()) == it
+        assert rel(float(out["res"][b].item()), st["res"]) < 1e-3
+        assert np.linalg.norm(U[b] - o.U) / np.linalg.norm(o.U) < TOL
+        # the quiet columns must carry exactly the lattice's iteration count as well
+        assert np.linalg.norm(U[b][:, :8] - o.U[:, :8]) / np.linalg.norm(o.U[:, :8]) < 1e-4
+        assert np.linalg.norm(Us[b] - ous) / np.linalg.norm(ous) < TOL
+        assert rel(float(out["deltaH"][b].item()), o.delta_h(ous)) < TOL
+
+
+def test_batched_unresolved_falls_back_to_global_pcg(monkeypatch):
+    """Host fallback (osc_pcg_solve per flagged lattice), forced through the test hook."""
+    from oscillink_b200 import BatchedLattices
+
+    B, N, D, k = 2, 200, 32, 5
+    Y, psi = _inputs(B, N, D, seed0=90)
+    ref = BatchedLattices(Y, kneighbors=k)
+    ref.set_query(psi)
+    want = ref.settle(receipt=True)
+    monkeypatch.setenv("OSC_BATCHED_FORCE_UNRESOLVED", "1")
+    bl = BatchedLattices(Y, kneighbors=k)
+    bl.set_query(psi)
+    lazy = bl.settle(receipt=True, strict=False)
+    assert (lazy["unresolved"].cpu().numpy() & 1).all()
+    assert bl.resolve_flagged(lazy) == B
+    assert not (lazy["unresolved"].cpu().numpy() & 1).any()
+    for key in ("iters", "ustar_iters"):
+        assert np.array_equal(lazy[key].cpu().numpy(), want[key].cpu().numpy())
+    assert np.allclose(lazy["deltaH"].cpu().numpy(), want["deltaH"].cpu().numpy(), rtol=1e-5)
+    U0, U1 = ref.U.cpu().numpy(), bl.U.cpu().numpy()
+    assert np.linalg.norm(U0 - U1) / np.linalg.norm(U0) < TOL
+
+
+def test_settle_host_batch_pipelined_matches_resident():
+    import torch
+
+    from oscillink_b200 import BatchedLattices, settle_host_batch
+
+    B, N, D, k = 7, 160, 32, 6
+    Y, psi = _inputs(B, N, D, seed0=120)
+    Yh = torch.from_numpy(Y).pin_memory()
+    ph = torch.from_numpy(psi).pin_memory()
+    got = settle_host_batch(Yh, ph, kneighbors=k, chunk=3).numpy()
+    bl = BatchedLattices(Y, kneighbors=k)
+    bl.set_query(psi)
+    out = bl.settle(receipt=True)
+    assert np.array_equal(got[:, 0], out["iters"].cpu().numpy().astype(np.float64))
+    assert np.array_equal(got[:, 2], out["ustar_iters"].cpu().numpy().astype(np.float64))
+    assert np.allclose(got[:, 4], out["deltaH"].cpu().numpy(), rtol=1e-12)
