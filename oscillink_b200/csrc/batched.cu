@@ -118,10 +118,19 @@ __device__ __forceinline__ void warp_reduce8(float4 a, float4 b, float4* red_a, 
   // b4 picks the vector (0: a, 1: b), component = b3*2 + b2
   if ((lane & 3) == 0) reinterpret_cast<float*>(b4 ? red_b : red_a)[b3 * 2 + b2] = kk;
 }
-__device__ __forceinline__ float4 block_total(const float4* red, int nw) {
-  float4 t = red[0];
-  for (int w = 1; w < nw; ++w) t = f4_add(t, red[w]);
-  return t;
+// Total of the nw per-warp partials, identical in every thread: lane l fetches component l&3 of
+// warps l>>2, (l>>2)+8, ... (conflict-free LDS.32), a 3-step butterfly over lane bits 2-4 finishes
+// the sum, and 4 SHFL hand every lane all four components.  (A broadcast LDS.128 costs 2 crossbar
+// wavefronts; reading all nw partials per thread was 15 % of the kernel's shared-memory traffic.)
+__device__ __forceinline__ float4 block_total(const float4* red, int nw, int lane) {
+  const float* rf = reinterpret_cast<const float*>(red);
+  float t = 0.f;
+  for (int i = lane; i < nw * 4; i += 32) t += rf[i];
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return make_float4(__shfl_sync(0xffffffffu, t, 0), __shfl_sync(0xffffffffu, t, 1),
+                     __shfl_sync(0xffffffffu, t, 2), __shfl_sync(0xffffffffu, t, 3));
 }
 
 template <int TPT>
@@ -155,7 +164,7 @@ __device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nb
 // (or at max_iters); forced > 0: run exactly `forced` iterations.  *rr_out = max_c ||r_c||^2 there.
 template <int TPT, int KQ>
 __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max_iters, int forced,
-                          int N, int kq, float4* p_s, const float2* rowc_s, const ushort4* nbr_s,
+                          int N, int kq, float4* p_s, const float* diag_s, const float* im_s, const ushort4* nbr_s,
                           const float4* w_s, float4* red, const bool (&act)[TPT], float* rr_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nw = T >> 5;
@@ -165,7 +174,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
 #pragma unroll
   for (int m = 0; m < TPT; ++m)
     if (act[m]) p_s[tid + T * m] = st.X[m];
-  __syncthreads();  // x0 visible; rowc_s of this solve visible
+  __syncthreads();  // x0 visible; diag_s, im_s of this solve visible
   // ---- r0 = b - A x0 ; z0 ; rz
   float4 z0[TPT];
   float4 part = f4_zero();
@@ -174,18 +183,18 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     z0[m] = f4_zero();
     if (act[m]) {
       const int row = tid + T * m;
-      const float2 rc = rowc_s[row];
-      const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, rc.x, c.offc);
+      const float imr = im_s[row];
+      const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, diag_s[row], c.offc);
       float4 r = st.R[m];
       r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
       st.R[m] = r;
-      z0[m] = make_float4(r.x * rc.y, r.y * rc.y, r.z * rc.y, r.w * rc.y);
+      z0[m] = make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr);
       part = f4_add(part, f4_mul(r, z0[m]));
     }
   }
   warp_reduce4(part, redA + warp, lane);
   __syncthreads();  // also: every gather of x0 has completed
-  float4 rz = block_total(redA, nw);
+  float4 rz = block_total(redA, nw, lane);
 #pragma unroll
   for (int m = 0; m < TPT; ++m)
     if (act[m]) p_s[tid + T * m] = z0[m];
@@ -200,13 +209,13 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     for (int m = 0; m < TPT; ++m) {
       if (act[m]) {
         const int row = tid + T * m;
-        st.AP[m] = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, rowc_s[row].x, c.offc);
+        st.AP[m] = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, diag_s[row], c.offc);
         part = f4_add(part, f4_mul(p_s[row], st.AP[m]));
       }
     }
     warp_reduce4(part, redA + warp, lane);
     __syncthreads();
-    const float4 pap = block_total(redA, nw);
+    const float4 pap = block_total(redA, nw, lane);
     const float4 alpha = make_float4(__fdiv_rn(rz.x, pap.x + 1e-18f), __fdiv_rn(rz.y, pap.y + 1e-18f),
                                      __fdiv_rn(rz.z, pap.z + 1e-18f), __fdiv_rn(rz.w, pap.w + 1e-18f));
     // ---- C: x, r update; rr and rz'
@@ -226,7 +235,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
                         fmaf(-ap.w, alpha.w, r.w));
         st.X[m] = x;
         st.R[m] = r;
-        const float im = rowc_s[row].y;
+        const float im = im_s[row];
         const float4 z = make_float4(r.x * im, r.y * im, r.z * im, r.w * im);
         zz[m] = z;
         prr = f4_add(prr, f4_mul(r, r));
@@ -235,8 +244,8 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     }
     warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
     __syncthreads();
-    const float4 rr = block_total(redB, nw);
-    const float4 rzn = block_total(redC, nw);
+    const float4 rr = block_total(redB, nw, lane);
+    const float4 rzn = block_total(redC, nw, lane);
     mx = fmaxf(fmaxf(rr.x, rr.y), fmaxf(rr.z, rr.w));
     // identical in every thread (same summation order) -> uniform branch
     const bool stop = forced > 0 ? (it >= forced)
@@ -362,7 +371,8 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
   float4* w_s = p_s + N;                                                // [kq][N]
   float4* red = w_s + (size_t)N * kq;                                   // 3 x RED_F4
   ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 3 * RED_F4);        // [kq][N]
-  float2* rowc_s = reinterpret_cast<float2*>(nbr_s + (size_t)N * kq);   // [N] (diag, 1/Mdiag)
+  float* diag_s = reinterpret_cast<float*>(nbr_s + (size_t)N * kq);      // [N] operator diagonal
+  float* im_s = diag_s + N;                                             // [N] 1/(Mdiag + 1e-12)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x;
@@ -414,10 +424,11 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         c.diag0 = 1.0f + P.dt * (P.lamG + P.lamC);
         c.diag1 = P.dt * P.lamQ;
         c.offc = P.dt * P.lamC;
-        __syncthreads();  // previous solve's readers of rowc_s / p_s are done
+        __syncthreads();  // previous solve's readers of diag_s, im_s, p_s are done
         for (int e = tid; e < N; e += T) {
           const float bq = gb ? gb[e] : 1.0f;
-          rowc_s[e] = make_float2(c.diag0 + c.diag1 * bq, __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f));
+          diag_s[e] = c.diag0 + c.diag1 * bq;
+          im_s[e] = __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f);
         }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           }
         }
         const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, N, kq, p_s,
-                                              rowc_s, nbr_s, w_s, red, act, &rr);
+                                              diag_s, im_s, nbr_s, w_s, red, act, &rr);
         if (Uo != nullptr) {
 #pragma unroll
           for (int m = 0; m < TPT; ++m)
@@ -454,10 +465,11 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         c.diag0 = P.lamG + P.lamC;
         c.diag1 = P.lamQ;
         c.offc = P.lamC;
-        __syncthreads();  // the settle solve's readers of rowc_s are done
+        __syncthreads();  // the settle solve's readers of diag_s, im_s are done
         for (int e = tid; e < N; e += T) {
           const float bq = gb ? gb[e] : 1.0f;
-          rowc_s[e] = make_float2(c.diag0 + c.diag1 * bq, __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f));
+          diag_s[e] = c.diag0 + c.diag1 * bq;
+          im_s[e] = __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f);
         }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           }
         }
         const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, N, kq, p_s,
-                                              rowc_s, nbr_s, w_s, red, act, &rr);
+                                              diag_s, im_s, nbr_s, w_s, red, act, &rr);
         if (P.Ustar_out != nullptr) {
           float* So = P.Ustar_out + b * (int64_t)N * P.D;
 #pragma unroll
@@ -503,15 +515,15 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
               const int row = tid + T * m;
-              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, rowc_s[row].x, c.offc);
+              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, diag_s[row], c.offc);
               part = f4_add(part, f4_mul(p_s[row], a));
             }
           }
           warp_reduce4(part, red + warp, lane);
           __syncthreads();
-          if (tid == 0) {
-            const float4 tot = block_total(red, T >> 5);
-            P.dh_part[b * P.G + s] = (double)((tot.x + tot.y) + (tot.z + tot.w));
+          if (warp == 0) {
+            const float4 tot = block_total(red, T >> 5, lane);
+            if (lane == 0) P.dh_part[b * P.G + s] = (double)((tot.x + tot.y) + (tot.z + tot.w));
           }
         }
       }

@@ -20,6 +20,8 @@
 // neighbour sets in the canonical order -- both engines therefore yield identical graphs.
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace osc {
@@ -32,7 +34,8 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // Ahi, Alo, Bhi, Blo
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_EPI_BYTES = 4 * 32 * 32 * 4;  // per epilogue warp: one 32x32 fp32 chunk
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_BYTES;
 
 struct TcParams {
   int64_t batch, n_rows, row0, N;
@@ -135,6 +138,67 @@ struct Pipe {
     }
   }
 };
+
+
+// ---------------------------------------------------------------- fused top-KC epilogue
+// Thread == TMEM lane == similarity row; the row's running top-KC list (sorted, descending) lives
+// in registers.  Scanning the 32 columns of a chunk one by one costs a full (divergent) insertion
+// whenever ANY of the 32 rows of the warp has a hit at that column -- at N ~ 1e3 that is almost
+// every column, and the epilogue, not the tensor pipe, bounded the kernel.  Instead every lane
+// first builds the bit mask of its columns above its own threshold, the chunk is parked in shared
+// memory, and the warp then runs insertion ROUNDS: in round r every lane inserts its r-th hit.
+// Lanes insert side by side, so the number of (expensive) insertion executions per chunk is the
+// maximum hit count over the 32 rows instead of the number of distinct hit columns (~4x fewer at
+// N = 1200, kc = 12).  Hits are taken in ascending column order and the test is a strict '>', so
+// the smaller column still wins ties.
+template <int KC>
+__device__ __forceinline__ void topk_insert(float (&val)[KC], int (&idx)[KC], float s, int col) {
+#pragma unroll
+  for (int q = KC - 1; q > 0; --q) {
+    const bool up = s > val[q - 1];
+    const bool here = !up && (s > val[q]);
+    const float nv = up ? val[q - 1] : (here ? s : val[q]);
+    const int ni = up ? idx[q - 1] : (here ? col : idx[q]);
+    val[q] = nv;
+    idx[q] = ni;
+  }
+  if (s > val[0]) {
+    val[0] = s;
+    idx[0] = col;
+  }
+}
+
+template <int KC>
+__device__ __forceinline__ void topk_chunk(float (&val)[KC], int (&idx)[KC], float (&v)[32], int c0, int N,
+                                           int self, bool row_ok, float* buf, int lane) {
+  // columns outside the lattice and the row's own column never qualify (warp-uniform fast path:
+  // the 32 rows of a warp are consecutive, so `self` falls into at most two chunks per row panel)
+  const bool self_here = __any_sync(0xffffffffu, self >= c0 && self < c0 + 32);  // all lanes vote
+  if (c0 + 32 > N || self_here) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i >= N || c0 + i == self) v[i] = -INFINITY;
+  }
+  const float thr = val[KC - 1];
+  unsigned mask = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (v[i] > thr) mask |= 1u << i;
+  if (!row_ok) mask = 0;
+  if (!__any_sync(0xffffffffu, mask != 0)) return;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) buf[i * 32 + lane] = v[i];
+  __syncwarp();
+  while (__any_sync(0xffffffffu, mask != 0)) {
+    if (mask != 0) {
+      const int e = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float s = buf[e * 32 + lane];
+      if (s > val[KC - 1]) topk_insert<KC>(val, idx, s, c0 + e);
+    }
+  }
+  __syncwarp();
+}
 
 // ---------------------------------------------------------------- kernel
 template <int KC>
@@ -239,6 +303,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant
     // ===================== epilogue: fused per-row top-KC
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int r_tile = quarter * 32 + lane;
+    float* ebuf = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 256) + quarter * 1024;
     Pipe acc;
     for (int64_t w = blockIdx.x; w < P.total_work; w += gridDim.x) {
       const int64_t b = w / P.panels;
@@ -264,29 +329,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant
           if (c0 >= P.N) break;  // warp-uniform
           float v[32];
           tmem_ld32(trow + (uint32_t)(ch * 32), v);
-          if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = c0 + i;
-              const float s = (col < P.N && col != self) ? v[i] : -INFINITY;
-              if (s > val[KC - 1]) {
-                // sorted insert (descending); strict '>' keeps the smaller column on ties
-#pragma unroll
-                for (int p = KC - 1; p > 0; --p) {
-                  const bool up = s > val[p - 1];
-                  const bool here = !up && (s > val[p]);
-                  const float nv = up ? val[p - 1] : (here ? s : val[p]);
-                  const int ni = up ? idx[p - 1] : (here ? col : idx[p]);
-                  val[p] = nv;
-                  idx[p] = ni;
-                }
-                if (s > val[0]) {
-                  val[0] = s;
-                  idx[0] = col;
-                }
-              }
-            }
-          }
+          topk_chunk<KC>(val, idx, v, c0, (int)P.N, self, row_ok, ebuf, lane);
         }
         tc_fence_before();
         mbar_arrive(tempty0 + 8 * acc.stage);
@@ -309,6 +352,227 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+
+// ================================================================= 2-CTA (cta_group::2) variant
+// Two CTAs of a cluster (one TPC) execute every MMA together: M = 256 rows (128 per CTA), N = 256.
+// Each CTA stages ITS 128 query rows and only HALF of the 256 column rows of a tile, so the
+// L2 -> shared-memory traffic per MMA drops from 96 KB to 64 KB per CTA and k-block -- this kernel
+// is bound by exactly that traffic (ncu: tensor pipe 29 % busy, xbar->L1 5 TB/s with one CTA per
+// tile).  The smaller stage also buys a third pipeline stage.
+//
+//   leader CTA (cluster rank 0): warp 1 issues tcgen05.mma.cta_group::2 for the pair
+//   both CTAs: warp 0 TMA producer (signals the LEADER's full barrier), warps 2..5 epilogue on
+//              their own TMEM half (128 lanes x 256 columns, double-buffered)
+//   tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogues of
+//   both CTAs arrive on the leader's "accumulator drained" barrier.
+constexpr int TC2_STAGES = 3;
+constexpr int TC2_HALF_BYTES = 128 * TC_BK * 4;                     // 128 rows x 32 floats
+constexpr int TC2_STAGE_BYTES = 4 * TC2_HALF_BYTES;                 // Ahi, Alo, Bhi(half), Blo(half)
+constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + TC_EPI_BYTES;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t dst, uint32_t cluster_bar,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+template <int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+               const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t bars = base + TC2_STAGES * TC2_STAGE_BYTES;
+  // barrier slots (8 B each): full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t full0 = bars, empty0 = bars + 8 * TC2_STAGES, tfull0 = bars + 16 * TC2_STAGES,
+                 tempty0 = tfull0 + 16;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(gen_base + TC2_STAGES * TC2_STAGE_BYTES + 16 * TC2_STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);   // leader's producer arrives with the byte count of BOTH CTAs
+      mbar_init(empty0 + 8 * s, 1);  // one multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 256);  // 128 epilogue threads of each CTA (used in the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation of both CTAs visible before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs)
+    if (lane == 0) {
+      Pipe p;
+      for (int64_t w = pair; w < P.total_work; w += n_pairs) {
+        const int b = (int)(w / P.panels);
+        const int m0 = (int)(w % P.panels) * 256 + (int)rank * 128;  // this CTA's 128 query rows
+        for (int ct = 0; ct < P.col_tiles; ++ct) {
+          const int n0 = ct * TC_BN + (int)rank * 128;               // this CTA's half of the column rows
+          for (int kb = 0; kb < P.k_blocks; ++kb) {
+            mbar_wait(empty0 + 8 * p.stage, p.phase ^ 1u);
+            const uint32_t sb = base + p.stage * TC2_STAGE_BYTES;
+            const uint32_t fb = mapa_rank(full0 + 8 * p.stage, 0);   // the leader's full barrier
+            if (leader) mbar_expect_tx(full0 + 8 * p.stage, 2 * TC2_STAGE_BYTES);
+            tma_load_3d_pair(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
+            tma_load_3d_pair(&tm_q_lo, sb + TC2_HALF_BYTES, fb, kb * TC_BK, m0, b);
+            tma_load_3d_pair(&tm_a_hi, sb + 2 * TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+            tma_load_3d_pair(&tm_a_lo, sb + 3 * TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+            p.advance(TC2_STAGES);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only)
+    if (leader) {
+      // instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=256 (pair)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      Pipe p, acc;
+      for (int64_t w = pair; w < P.total_work; w += n_pairs) {
+        for (int ct = 0; ct < P.col_tiles; ++ct) {
+          mbar_wait(tempty0 + 8 * acc.stage, acc.phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + (uint32_t)(acc.stage * TC_BN);
+          for (int kb = 0; kb < P.k_blocks; ++kb) {
+            mbar_wait(full0 + 8 * p.stage, p.phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sb = base + p.stage * TC2_STAGE_BYTES;
+              const uint64_t ah = umma_desc(sb), al = umma_desc(sb + TC2_HALF_BYTES),
+                             bh = umma_desc(sb + 2 * TC2_HALF_BYTES), bl = umma_desc(sb + 3 * TC2_HALF_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                const uint64_t o = (uint64_t)((ks * 32) >> 4);
+                tc_mma_tf32_pair(tacc, al + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
+                tc_mma_tf32_pair(tacc, ah + o, bl + o, idesc, 1u);
+                tc_mma_tf32_pair(tacc, ah + o, bh + o, idesc, 1u);
+              }
+              tc_commit_pair(empty0 + 8 * p.stage);  // stage free in BOTH CTAs once these MMAs retire
+              if (kb == P.k_blocks - 1) tc_commit_pair(tfull0 + 8 * acc.stage);
+            }
+            __syncwarp();
+            p.advance(TC2_STAGES);
+          }
+          acc.advance(2);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: fused per-row top-KC on this CTA's 128 rows
+    const int quarter = warp & 3;
+    const int r_tile = quarter * 32 + lane;
+    float* ebuf = reinterpret_cast<float*>(gen_base + TC2_STAGES * TC2_STAGE_BYTES + 256) + quarter * 1024;
+    const uint32_t tempty_leader0 = mapa_rank(tempty0, 0);
+    Pipe acc;
+    for (int64_t w = pair; w < P.total_work; w += n_pairs) {
+      const int64_t b = w / P.panels;
+      const int m0 = (int)(w % P.panels) * 256 + (int)rank * 128;
+      const int gi = m0 + r_tile;
+      const int self = (int)(P.row0 + gi);
+      const bool row_ok = gi < P.n_rows;
+      float val[KC];
+      int idx[KC];
+#pragma unroll
+      for (int i = 0; i < KC; ++i) {
+        val[i] = -INFINITY;
+        idx[i] = -1;
+      }
+      for (int ct = 0; ct < P.col_tiles; ++ct) {
+        const int n0 = ct * TC_BN;
+        mbar_wait(tfull0 + 8 * acc.stage, acc.phase);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc.stage * TC_BN);
+#pragma unroll 1
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          const int c0 = n0 + ch * 32;
+          if (c0 >= P.N) break;  // warp-uniform
+          float v[32];
+          tmem_ld32(trow + (uint32_t)(ch * 32), v);
+          topk_chunk<KC>(val, idx, v, c0, (int)P.N, self, row_ok, ebuf, lane);
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(tempty_leader0 + 8 * acc.stage);
+        acc.advance(2);
+      }
+      if (row_ok) {
+        const int64_t o = (b * P.n_rows + gi) * P.kc;
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+          if (i < P.kc) {
+            P.cand_idx[o + i] = idx[i];
+            P.cand_sim[o + i] = val[i];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory / barriers stay alive until every MMA and commit landed
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -359,12 +623,18 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
   if (!knn_tc_supported(N, D, kc)) return fail(OSC_ERR_UNSUPPORTED, "knn_tc: shape not covered");
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   OSC_REQUIRE(a16(q_hi) && a16(q_lo) && a16(all_hi) && a16(all_lo), "knn_tc: operands must be 16 B aligned");
+  const int64_t sms = sm_count();
+  bool pair = n_rows > TC_BM && sms >= 2;
+  {
+    const char* e = getenv("OSC_KNN_TC_PAIR");  // dev-only A/B switch: 0 = one CTA per tile
+    if (e) pair = pair && atoi(e) != 0;
+  }
   CUtensorMap mqh, mql, mah, mal;
   int rc;
   if ((rc = make_map(&mqh, q_hi, batch, n_rows, D, TC_BM))) return rc;
   if ((rc = make_map(&mql, q_lo, batch, n_rows, D, TC_BM))) return rc;
-  if ((rc = make_map(&mah, all_hi, batch, N, D, TC_BN))) return rc;
-  if ((rc = make_map(&mal, all_lo, batch, N, D, TC_BN))) return rc;
+  if ((rc = make_map(&mah, all_hi, batch, N, D, pair ? 128 : TC_BN))) return rc;
+  if ((rc = make_map(&mal, all_lo, batch, N, D, pair ? 128 : TC_BN))) return rc;
   TcParams P;
   P.batch = batch;
   P.n_rows = n_rows;
@@ -372,21 +642,42 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
   P.N = N;
   P.D = D;
   P.kc = kc;
-  P.panels = (int)((n_rows + TC_BM - 1) / TC_BM);
+  P.panels = (int)((n_rows + (pair ? 256 : TC_BM) - 1) / (pair ? 256 : TC_BM));
   P.col_tiles = (int)((N + TC_BN - 1) / TC_BN);
   P.k_blocks = (D + TC_BK - 1) / TC_BK;
   P.total_work = batch * P.panels;
   P.cand_idx = cand_idx;
   P.cand_sim = cand_sim;
-  const int64_t sms = sm_count();
-  const unsigned grid = (unsigned)(P.total_work < sms ? P.total_work : sms);
-  if (kc <= 16) {
-    OSC_CUDA(cudaFuncSetAttribute(knn_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    knn_tc_kernel<16><<<grid, TC_THREADS, TC_SMEM, st>>>(mqh, mql, mah, mal, P);
-  } else {
-    OSC_CUDA(cudaFuncSetAttribute(knn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    knn_tc_kernel<32><<<grid, TC_THREADS, TC_SMEM, st>>>(mqh, mql, mah, mal, P);
+  if (pair) {
+    int64_t pairs = sms / 2;
+    if (P.total_work < pairs) pairs = P.total_work;
+    const unsigned grid = (unsigned)(2 * pairs);
+#define OSC_TC2_LAUNCH(K)                                                                                  \
+  do {                                                                                                     \
+    OSC_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM)); \
+    knn_tc2_kernel<K><<<grid, TC_THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);                           \
+  } while (0)
+    if (kc <= 8) OSC_TC2_LAUNCH(8);
+    else if (kc <= 12) OSC_TC2_LAUNCH(12);
+    else if (kc <= 16) OSC_TC2_LAUNCH(16);
+    else if (kc <= 24) OSC_TC2_LAUNCH(24);
+    else OSC_TC2_LAUNCH(32);
+#undef OSC_TC2_LAUNCH
+    OSC_LAUNCH_CHECK("knn_tc2_kernel");
+    return OSC_OK;
   }
+  const unsigned grid = (unsigned)(P.total_work < sms ? P.total_work : sms);
+#define OSC_TC_LAUNCH(K)                                                                                 \
+  do {                                                                                                   \
+    OSC_CUDA(cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); \
+    knn_tc_kernel<K><<<grid, TC_THREADS, TC_SMEM, st>>>(mqh, mql, mah, mal, P);                           \
+  } while (0)
+  if (kc <= 8) OSC_TC_LAUNCH(8);
+  else if (kc <= 12) OSC_TC_LAUNCH(12);
+  else if (kc <= 16) OSC_TC_LAUNCH(16);
+  else if (kc <= 24) OSC_TC_LAUNCH(24);
+  else OSC_TC_LAUNCH(32);
+#undef OSC_TC_LAUNCH
   OSC_LAUNCH_CHECK("knn_tc_kernel");
   return OSC_OK;
 }
