@@ -321,6 +321,169 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- large single lattice
+def run_large(args) -> None:
+    """BASELINE.json configs[3]/[4]: ONE big lattice (N up to 10M), kNN build + PCG settle, the rows
+    (or column slabs) partitioned over the GPUs.  A step = one settle(12, 1e-3) from U = Y on the built
+    lattice (the metric's `ms/settle`); build, U* + deltaH and the per-kernel rooflines ride along."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oscillink_b200 import _cabi
+    from oscillink_b200.sharded_api import ShardedLattice, _NativeKernels, gather_rows, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, D, k = args.N, args.D, args.k
+    row0, n_local, _ = shard_bounds(N, world, rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    Y_local = torch.randn((n_local, D), generator=gen, device=dev, dtype=torch.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat = ShardedLattice(Y_local, N, kneighbors=k, mode=args.partition)
+    e1.record()
+    barrier()
+    build_ms = max_over_ranks(e0.elapsed_time(e1))
+    head = Y_local[:32].mean(dim=0)
+    if world > 1:
+        dist.broadcast(head, src=0)
+    psi = (head / (head.norm() + 1e-12)).cpu().numpy()
+    psi_host = torch.from_numpy(psi.copy()).pin_memory()
+    lat.set_query(psi)
+    if args.chain_len >= 2:
+        lat.add_chain(list(range(args.chain_len)), lamP=0.2)
+    Y0 = lat._Y
+
+    def one_settle():
+        lat._U = Y0.clone()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lat.set_query(psi_host.numpy())          # host psi -> device (the request's only host input)
+        st = lat.settle(max_iters=12, tol=1e-3)  # returns host {iters,res}: D2H inside
+        b.record()
+        barrier()
+        return a.elapsed_time(b), st
+
+    for _ in range(max(args.warmup, 1)):
+        one_settle()
+    with ClockSampler(local) as clk:
+        tot, st = 0.0, None
+        for _ in range(args.steps):
+            ms, st = one_settle()
+            tot += ms
+    clocks = clk.summary()
+    ms_settle = max_over_ranks(tot / args.steps)
+
+    barrier()
+    e0.record()
+    rec = lat.receipt()
+    e1.record()
+    barrier()
+    receipt_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- per-kernel timings on the live state (one rank-local launch each, CUDA events)
+    Dl = D if args.partition == "rows" else lat.Dl
+    n_loc = n_local if args.partition == "rows" else N
+    X = lat._U.clone()
+    kf = _NativeKernels(lat, _cabi.MODE_SETTLE, 1.0, True, X, lat._Y.clone())
+    ones = torch.ones(Dl, dtype=torch.float32, device=dev)
+
+    def t_of(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    full = (lambda v: gather_rows(v, N, lat.group).contiguous()) if args.partition == "rows" else (lambda v: v)
+    x_all = full(X)
+    kf.residual0(x_all)
+    p_all = full(kf.P)
+    nnz = float(lat.nnz.item())
+    nnz_loc = nnz * n_loc / max(N, 1) if args.partition == "rows" else nnz
+    V = n_loc * Dl * 4.0
+    kms = {
+        "pcg_spmm": t_of(lambda: kf.spmm(p_all)),
+        "pcg_update": t_of(lambda: kf.update(ones, ones)),
+        "pcg_pupdate": t_of(lambda: kf.pupdate(ones, ones)),
+    }
+    if world > 1 and args.partition == "rows":
+        kms["halo_allgather_p"] = t_of(lambda: full(kf.P))
+    alg = {  # SURVEY 8(d): algorithmic bytes per launch
+        "pcg_spmm": (nnz_loc / max(n_loc, 1) + 2.0) * V + 8.0 * nnz_loc,
+        "pcg_update": 6.0 * V,
+        "pcg_pupdate": 3.0 * V,
+    }
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_src = "measured"
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0}
+        peak_src = "fallback"
+    peak = float(peaks["hbm_gbs"])
+    gbs = {n: alg[n] / (kms[n] / 1000.0) / 1e9 for n in alg}
+    iters = int(st["iters"])
+    iter_bytes = alg["pcg_spmm"] + alg["pcg_update"] + alg["pcg_pupdate"]
+    solve_bytes = (iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"] + (iters - 1) * alg["pcg_pupdate"] + 4.0 * V
+    roof = {"kernel": "pcg_spmm_kernel", "bound": "hbm", "achieved": gbs["pcg_spmm"], "peak": peak,
+            "unit": "GB/s", "frac": gbs["pcg_spmm"] / peak, "traffic": None, "peak_source": peak_src,
+            "kernel_ms": kms, "kernel_gbs": gbs,
+            "whole_settle": {"algorithmic_bytes": solve_bytes, "achieved_gbs": solve_bytes / (ms_settle / 1e3) / 1e9,
+                             "frac": solve_bytes / (ms_settle / 1e3) / 1e9 / peak},
+            "bytes_per_iteration": iter_bytes}
+    if rank == 0:
+        line = {
+            "metric": f"ms/settle at N={N},D={D}", "value": ms_settle, "unit": "ms", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_settle,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"one lattice N={N} D={D} k={k} chain_len={args.chain_len}: "
+                                   "step = settle(12,1e-3) from U=Y on the built mutual-kNN graph",
+                       "parallelism": f"{args.partition} x{world}",
+                       "l2": f"vectors ({V / 1e9:.2f} GB each per GPU) larger than L2"},
+            "e2e": {"value": ms_settle, "unit": "ms", "h2d_bytes_per_step": int(D * 4),
+                    "d2h_bytes_per_step": 8,
+                    "note": "set_query(host psi) + settle() -> host {iters,res}; the lattice state is device-resident by API"},
+            "gpu_launches": int(2 + 6 * iters) * args.steps,
+            "clocks": clocks, "roofline": roof,
+            "build_ms": build_ms, "receipt_light_ms": receipt_ms,
+            "check": {"iters": iters, "res": float(st["res"]), "ustar_iters": rec["meta"]["ustar_iters"],
+                      "ustar_res": rec["meta"]["ustar_res"], "deltaH": rec["deltaH_total"],
+                      "avg_degree": rec["meta"]["avg_degree"], "nnz": nnz},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,9 +492,18 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="lattices per step per GPU")
     ap.add_argument("--chunk", type=int, default=512, help="lattices per H2D/compute pipeline stage (e2e)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="serving", choices=["serving", "large"],
+                    help="serving: the headline batch of N=1200 lattices; large: one big lattice (ms/settle)")
+    ap.add_argument("--N", type=int, default=1_000_000)
+    ap.add_argument("--D", type=int, default=768)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--chain-len", type=int, default=0)
+    ap.add_argument("--partition", default="rows", choices=["rows", "columns"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "large":
+        run_large(args)
     else:
         run_ours(args)
 

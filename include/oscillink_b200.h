@@ -199,6 +199,16 @@ int osc_pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_para
                   const float* gates, int32_t D, float* X, int32_t* h_iters, float* h_res,
                   void* workspace, size_t ws_bytes, void* stream);
 
+/* The same recurrences for a caller-supplied start vector and right-hand side: on entry X = x0
+ * ([N][D]) and B = right-hand side (clobbered with the residual).  This is the solve behind
+ * compute_diffusion_gates (oscillink/preprocess/diffusion.py:132-150): with lamG = gamma,
+ * lamC = 1, lamQ = 0 the stationary operator is exactly L_sym + gamma*I.  Workspace from
+ * osc_pcg_plan. */
+int osc_pcg_solve_system(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm,
+                         int32_t mode, float dt, int32_t jacobi, double tol, int32_t max_iters,
+                         const float* gates, int32_t D, float* X, float* B, int32_t* h_iters,
+                         float* h_res, void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ K4: receipts
  * deltaH = <U-U*, M (U-U*)>  (receipts.py:21-25).  workspace from osc_pcg_plan. */
 int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm,

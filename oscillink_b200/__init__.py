@@ -22,6 +22,10 @@ def __getattr__(name):  # lazy: torch / the native library load only when the AP
         from . import batched_api
 
         return getattr(batched_api, name)
+    if name == "compute_diffusion_gates":
+        from . import diffusion
+
+        return diffusion.compute_diffusion_gates
     if name in {"ShardedLattice"}:
         from . import sharded_api
 
@@ -29,5 +33,6 @@ def __getattr__(name):  # lazy: torch / the native library load only when the AP
     raise AttributeError(name)
 
 
-__all__ = ["OscillinkLattice", "Oscillink", "BatchedLattices", "settle_host_batch", "ShardedLattice", "verify_receipt",
+__all__ = ["OscillinkLattice", "Oscillink", "BatchedLattices", "settle_host_batch", "ShardedLattice", "compute_diffusion_gates",
+           "verify_receipt",
            "verify_receipt_mode", "json_line_logger", "__version__"]

@@ -83,6 +83,9 @@ PROTOTYPES = {
     "osc_pcg_solve": (C.c_int, [P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32, c_f32, c_i32, c_f64,
                                 c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, P(c_i32),
                                 P(c_f32), c_void_p, c_size_t, c_void_p]),
+    "osc_pcg_solve_system": (C.c_int, [P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32, c_f64, c_i32,
+                                       c_void_p, c_i32, c_void_p, c_void_p, P(c_i32), P(c_f32), c_void_p,
+                                       c_size_t, c_void_p]),
     "osc_delta_h": (C.c_int, [P(Graph), P(Chain), P(Params), c_void_p, c_void_p, c_void_p, c_i32,
                               P(c_f64), c_void_p, c_size_t, c_void_p]),
     "osc_receipt_full": (C.c_int, [P(Graph), P(Params), c_void_p, c_void_p, c_void_p, c_void_p, c_i32,

@@ -62,6 +62,8 @@ int pcg_pupdate(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, con
 int pcg_solve(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, int, float, int, float, int,
               double, int, const float*, const float*, const float*, const float*, int, float*, int*,
               float*, void*, size_t, cudaStream_t);
+int pcg_solve_system(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, int, float, int, double,
+                     int, const float*, int, float*, float*, int*, float*, void*, size_t, cudaStream_t);
 int delta_h(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, const float*, const float*,
             const float*, int, double*, void*, size_t, cudaStream_t);
 int launch_receipt_full(const osc_graph_t*, const osc_params_t*, const float*, const float*,
@@ -302,6 +304,14 @@ int osc_pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_para
                   void* workspace, size_t ws_bytes, void* stream) {
   return pcg_solve(g, chain, prm, mode, dt, warm_start, inertia, jacobi, tol, max_iters, Y, U, psi, gates,
                    D, X, h_iters, h_res, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int osc_pcg_solve_system(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm,
+                         int32_t mode, float dt, int32_t jacobi, double tol, int32_t max_iters,
+                         const float* gates, int32_t D, float* X, float* B, int32_t* h_iters,
+                         float* h_res, void* workspace, size_t ws_bytes, void* stream) {
+  return pcg_solve_system(g, chain, prm, mode, dt, jacobi, tol, max_iters, gates, D, X, B, h_iters, h_res,
+                          workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, const float* U,

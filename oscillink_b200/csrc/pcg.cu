@@ -140,6 +140,14 @@ struct ChainView {
 
 // RES0 = false: AP = Aop(V); part = sum_i V_i * AP_i
 // RES0 = true : R  = Bv - Aop(V) (in place over RBv); P = precond(R); part = sum_i R_i * Z_i
+//
+// A block owns a contiguous row range and walks it in chunks of SPMM_RCH rows: the chunk's
+// neighbour ids / weights / degrees are staged in shared memory with one coalesced pass, so the
+// gather loop has no dependent index load in front of every row fetch and can keep 8 row fetches
+// per thread in flight (the kernel is latency-bound on random 4*D-byte rows otherwise).
+// blockIdx.y selects the 256-column-group panel when D/VEC > 256.
+constexpr int SPMM_RCH = 32;
+
 template <int VEC, bool RES0>
 __global__ void __launch_bounds__(256)
 pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
@@ -147,78 +155,114 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
                 double* __restrict__ part) {
   extern __shared__ double sh[];
   const int CG = dm.D / VEC;
+  const int nthr = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  int32_t* s_nb = reinterpret_cast<int32_t*>(sh + (size_t)nthr * VEC);
+  float* s_w = reinterpret_cast<float*>(s_nb + SPMM_RCH * g.k);
+  int32_t* s_deg = reinterpret_cast<int32_t*>(s_w + SPMM_RCH * g.k);
   const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
   const int64_t r_beg = (int64_t)blockIdx.x * rpb;
   const int64_t r_end = min(dm.n_local, r_beg + rpb);
   const float offc = op_offc(c), offp = op_offp(c);
-  for (int cg = threadIdx.x; cg < (CG + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
-       cg += blockDim.x) {
-    double acc[VEC];
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool col_ok = cg < CG;
+  const int co = cg * VEC;
+  double acc[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-    if (cg < CG) {
-      const int co = cg * VEC;
-      for (int64_t i = r_beg + threadIdx.y; i < r_end; i += blockDim.y) {
-        const int64_t gi = dm.row0 + i;
-        float own[VEC], s[VEC];
-        ldv<VEC>(Vall + gi * dm.D + co, own);
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+  for (int64_t c0 = r_beg; c0 < r_end; c0 += SPMM_RCH) {
+    const int rows = (int)min((int64_t)SPMM_RCH, r_end - c0);
+    __syncthreads();  // the previous chunk's readers are done
+    for (int e = tid; e < rows * g.k; e += nthr) {
+      s_nb[e] = g.nbr[c0 * g.k + e];
+      s_w[e] = g.W[c0 * g.k + e];
+    }
+    for (int e = tid; e < rows; e += nthr) s_deg[e] = g.deg[c0 + e];
+    __syncthreads();
+    if (!col_ok) continue;
+    for (int lr = threadIdx.y; lr < rows; lr += blockDim.y) {
+      const int64_t i = c0 + lr;
+      const int64_t gi = dm.row0 + i;
+      float own[VEC], s[VEC];
+      ldv<VEC>(Vall + gi * dm.D + co, own);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) s[v] = 0.f;
-        const int n = g.deg[i];
-        const int32_t* nb = g.nbr + i * g.k;
-        const float* wt = g.W + i * g.k;
-#pragma unroll 4
-        for (int t = 0; t < n; ++t) {
-          const int64_t j = nb[t];
-          const float w = wt[t];
-          float x[VEC];
-          ldv<VEC>(Vall + j * dm.D + co, x);
+      for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+      const int n = s_deg[lr];
+      const int32_t* nb = s_nb + lr * g.k;
+      const float* wt = s_w + lr * g.k;
+      int t = 0;
+      for (; t + 8 <= n; t += 8) {
+        float x[8][VEC];
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[v], s[v]);
-        }
-        const float b = gates ? gates[i] : 1.0f;
-        const float dg = op_diag(c, b);
-        float o[VEC];
+        for (int u = 0; u < 8; ++u) ldv<VEC>(Vall + (int64_t)nb[t + u] * dm.D + co, x[u]);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) o[v] = dg * own[v] - offc * s[v];
-        if (ch.slot != nullptr && offp != 0.f) {
-          const int sl = ch.slot[gi];
-          if (sl >= 0) {
-            float sp[VEC];
+        for (int u = 0; u < 8; ++u) {
+          const float w = wt[t + u];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) sp[v] = 0.f;
-            for (int e = ch.rowptr[sl]; e < ch.rowptr[sl + 1]; ++e) {
-              float x[VEC];
-              ldv<VEC>(Vall + (int64_t)ch.col[e] * dm.D + co, x);
-              const float w = ch.Wp[e];
-#pragma unroll
-              for (int v = 0; v < VEC; ++v) sp[v] = fmaf(w, x[v], sp[v]);
-            }
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) o[v] -= offp * sp[v];
-          }
-        }
-        if constexpr (RES0) {
-          float bv[VEC], r[VEC], z[VEC];
-          ldv<VEC>(out + i * dm.D + co, bv);
-          const float md = md_diag(c, b);
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            r[v] = bv[v] - o[v];
-            z[v] = precond(c, r[v], md);
-            acc[v] += (double)r[v] * (double)z[v];
-          }
-          stv<VEC>(out + i * dm.D + co, r);
-          stv<VEC>(Pout + i * dm.D + co, z);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] += (double)own[v] * (double)o[v];
-          stv<VEC>(out + i * dm.D + co, o);
+          for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
         }
       }
+      if (t + 4 <= n) {
+        float x[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ldv<VEC>(Vall + (int64_t)nb[t + u] * dm.D + co, x[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = wt[t + u];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+        }
+        t += 4;
+      }
+      for (; t < n; ++t) {
+        float x[VEC];
+        ldv<VEC>(Vall + (int64_t)nb[t] * dm.D + co, x);
+        const float w = wt[t];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[v], s[v]);
+      }
+      const float b = gates ? gates[i] : 1.0f;
+      const float dg = op_diag(c, b);
+      float o[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = dg * own[v] - offc * s[v];
+      if (ch.slot != nullptr && offp != 0.f) {
+        const int sl = ch.slot[gi];
+        if (sl >= 0) {
+          float sp[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) sp[v] = 0.f;
+          for (int e = ch.rowptr[sl]; e < ch.rowptr[sl + 1]; ++e) {
+            float x[VEC];
+            ldv<VEC>(Vall + (int64_t)ch.col[e] * dm.D + co, x);
+            const float w = ch.Wp[e];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sp[v] = fmaf(w, x[v], sp[v]);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) o[v] -= offp * sp[v];
+        }
+      }
+      if constexpr (RES0) {
+        float bv[VEC], r[VEC], z[VEC];
+        ldv<VEC>(out + i * dm.D + co, bv);
+        const float md = md_diag(c, b);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          r[v] = bv[v] - o[v];
+          z[v] = precond(c, r[v], md);
+          acc[v] += (double)r[v] * (double)z[v];
+        }
+        stv<VEC>(out + i * dm.D + co, r);
+        stv<VEC>(Pout + i * dm.D + co, z);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += (double)own[v] * (double)o[v];
+        stv<VEC>(out + i * dm.D + co, o);
+      }
     }
-    flush_partial<VEC>(acc, sh, part, dm.D, cg, cg < CG);
   }
+  flush_partial<VEC>(acc, sh, part, dm.D, cg, col_ok);
 }
 
 // ---------------------------------------------------------------- x, r update + partial rr, rz'
@@ -233,39 +277,38 @@ pcg_update_kernel(Dims dm, Coef c, const float* __restrict__ gates, const float*
   const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
   const int64_t r_beg = (int64_t)blockIdx.x * rpb;
   const int64_t r_end = min(dm.n_local, r_beg + rpb);
-  for (int cg = threadIdx.x; cg < (CG + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
-       cg += blockDim.x) {
-    double arr[VEC], arz[VEC];
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool col_ok = cg < CG;
+  double arr[VEC], arz[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) arr[v] = arz[v] = 0.0;
-    if (cg < CG) {
-      const int co = cg * VEC;
-      float alpha[VEC];
+  for (int v = 0; v < VEC; ++v) arr[v] = arz[v] = 0.0;
+  if (col_ok) {
+    const int co = cg * VEC;
+    float alpha[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) alpha[v] = __fdiv_rn(rz[co + v], pap[co + v] + 1e-18f);
-      for (int64_t i = r_beg + threadIdx.y; i < r_end; i += blockDim.y) {
-        const int64_t o = i * dm.D + co;
-        float p[VEC], ap[VEC], x[VEC], r[VEC];
-        ldv<VEC>(P + o, p);
-        ldv<VEC>(AP + o, ap);
-        ldv<VEC>(X + o, x);
-        ldv<VEC>(R + o, r);
-        const float md = md_diag(c, gates ? gates[i] : 1.0f);
+    for (int v = 0; v < VEC; ++v) alpha[v] = __fdiv_rn(rz[co + v], pap[co + v] + 1e-18f);
+    for (int64_t i = r_beg + threadIdx.y; i < r_end; i += blockDim.y) {
+      const int64_t o = i * dm.D + co;
+      float p[VEC], ap[VEC], x[VEC], r[VEC];
+      ldv<VEC>(P + o, p);
+      ldv<VEC>(AP + o, ap);
+      ldv<VEC>(X + o, x);
+      ldv<VEC>(R + o, r);
+      const float md = md_diag(c, gates ? gates[i] : 1.0f);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          x[v] = __fadd_rn(x[v], __fmul_rn(p[v], alpha[v]));
-          r[v] = __fsub_rn(r[v], __fmul_rn(ap[v], alpha[v]));
-          const float z = precond(c, r[v], md);
-          arr[v] += (double)r[v] * (double)r[v];
-          arz[v] += (double)r[v] * (double)z;
-        }
-        stv<VEC>(X + o, x);
-        stv<VEC>(R + o, r);
+      for (int v = 0; v < VEC; ++v) {
+        x[v] = __fadd_rn(x[v], __fmul_rn(p[v], alpha[v]));
+        r[v] = __fsub_rn(r[v], __fmul_rn(ap[v], alpha[v]));
+        const float z = precond(c, r[v], md);
+        arr[v] += (double)r[v] * (double)r[v];
+        arz[v] += (double)r[v] * (double)z;
       }
+      stv<VEC>(X + o, x);
+      stv<VEC>(R + o, r);
     }
-    flush_partial<VEC>(arr, sh, part_rr, dm.D, cg, cg < CG);
-    flush_partial<VEC>(arz, sh, part_rz, dm.D, cg, cg < CG);
   }
+  flush_partial<VEC>(arr, sh, part_rr, dm.D, cg, col_ok);
+  flush_partial<VEC>(arz, sh, part_rz, dm.D, cg, col_ok);
 }
 
 // ---------------------------------------------------------------- p = z + beta p
@@ -304,39 +347,50 @@ __global__ void diff_kernel(const float* __restrict__ a, const float* __restrict
 }
 
 // ---------------------------------------------------------------- column reduction of partials
+// out[c] = sum_b part[b][c] in a FIXED order (32 row lanes stride the row blocks, then a fixed
+// 32-term sum): run-to-run deterministic, which the knife-edge stop test needs.
+// One block per 32 columns; the lattice-wide max is merged with an order-independent atomicMax
+// on the bit pattern (values are >= 0; *d_max is zeroed by the host wrapper beforehand).
 __global__ void __launch_bounds__(1024)
 pcg_reduce_kernel(const double* __restrict__ part, int n_blocks, int D, float* __restrict__ out,
-                  float* __restrict__ d_max, double* __restrict__ d_total) {
-  __shared__ float smax[32];
-  __shared__ double ssum[32];
+                  float* __restrict__ d_max, double* __restrict__ out64) {
+  __shared__ double ssum[32][33];
+  const int cx = threadIdx.x, ry = threadIdx.y;
+  const int cidx = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (cidx < D)
+    for (int b = ry; b < n_blocks; b += 32) s += part[(size_t)b * D + cidx];
+  ssum[ry][cx] = s;
+  __syncthreads();
+  if (ry != 0) return;
+  double t = 0.0;
+#pragma unroll
+  for (int y = 0; y < 32; ++y) t += ssum[y][cx];
   float mx = 0.f;
-  double tot = 0.0;
-  for (int cidx = threadIdx.x; cidx < D; cidx += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += part[(size_t)b * D + cidx];
-    const float f = (float)s;
+  if (cidx < D) {
+    const float f = (float)t;
     out[cidx] = f;
-    mx = fmaxf(mx, __fsqrt_rn(fmaxf(f, 0.f)));
-    tot += s;
+    if (out64 != nullptr) out64[cidx] = t;
+    mx = __fsqrt_rn(fmaxf(f, 0.f));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  tot = warp_sum(tot);
-  if ((threadIdx.x & 31) == 0) {
-    smax[threadIdx.x >> 5] = mx;
-    ssum[threadIdx.x >> 5] = tot;
-  }
+  if (cx == 0 && d_max != nullptr) atomicMax(reinterpret_cast<int*>(d_max), __float_as_int(mx));
+}
+
+// fixed-order total of D doubles (deltaH)
+__global__ void __launch_bounds__(1024) sum_doubles_kernel(const double* __restrict__ v, int D,
+                                                          double* __restrict__ total) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s += v[i];
+  sh[threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = 0.f;
-    double t = 0.0;
-    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) {
-      m = fmaxf(m, smax[w]);
-      t += ssum[w];
-    }
-    if (d_max != nullptr) *d_max = m;
-    if (d_total != nullptr) *d_total = t;
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) *total = sh[0];
 }
 
 // ================================================================= host side
@@ -433,12 +487,14 @@ static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
     if (vec == 4) return fail(OSC_ERR_INVALID, "pcg: vectors must be 16-byte aligned when D % 4 == 0");
   }
   Coef c = make_coef(prm, mode, dt, jacobi);
-  const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double);
+  const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double) +
+                      (size_t)SPMM_RCH * (g->k * 8 + 4);
+  const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
   if (res0) {
-    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, true><<<d->n_blocks, blk, smem, st>>>(
+    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, true><<<grid, blk, smem, st>>>(
                               to_dims(d), c, gview(g), cview(chain), gates, Vall, out, Pout, part);)
   } else {
-    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, false><<<d->n_blocks, blk, smem, st>>>(
+    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, false><<<grid, blk, smem, st>>>(
                               to_dims(d), c, gview(g), cview(chain), gates, Vall, out, Pout, part);)
   }
   OSC_LAUNCH_CHECK("pcg_spmm_kernel");
@@ -457,10 +513,10 @@ int pcg_spmm_dot(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_
   return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, Pall, AP, nullptr, part_pap, st);
 }
 
-int pcg_reduce(const double* part, int n_blocks, int D, float* out, float* d_max, double* d_total,
+int pcg_reduce(const double* part, int n_blocks, int D, float* out, float* d_max, double* out64,
                cudaStream_t st) {
-  const int threads = D < 1024 ? ((D + 31) / 32 * 32) : 1024;
-  pcg_reduce_kernel<<<1, threads, 0, st>>>(part, n_blocks, D, out, d_max, d_total);
+  if (d_max != nullptr) OSC_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), st));
+  pcg_reduce_kernel<<<(D + 31) / 32, dim3(32, 32, 1), 0, st>>>(part, n_blocks, D, out, d_max, out64);
   OSC_LAUNCH_CHECK("pcg_reduce_kernel");
   return OSC_OK;
 }
@@ -475,7 +531,8 @@ int pcg_update(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float
   block_shape(d->D, vec, blk);
   Coef c = make_coef(prm, mode, dt, jacobi);
   const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double);
-  OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC><<<d->n_blocks, blk, smem, st>>>(
+  const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
+  OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC><<<grid, blk, smem, st>>>(
                             to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz);)
   OSC_LAUNCH_CHECK("pcg_update_kernel");
   return OSC_OK;
@@ -496,6 +553,50 @@ int pcg_pupdate(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, floa
   return OSC_OK;
 }
 
+// The recurrences of solver.py:19-37 from a caller-supplied start: on entry X = x0 and R = right-hand
+// side; on exit X = last iterate, R = recurrence residual.  Workspace: P, AP, partials, column sums.
+static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_chain_t* chain,
+                    const osc_params_t* prm, int mode, float dt, int jacobi, double tol, int max_iters,
+                    const float* gates, float* X, float* R, Arena& ar, int* h_iters, float* h_res,
+                    cudaStream_t st) {
+  const int D = d.D;
+  const size_t nd = (size_t)g->N * D;
+  float* P = ar.take<float>(nd);
+  float* AP = ar.take<float>(nd);
+  double* part_a = ar.take<double>((size_t)d.n_blocks * D);
+  double* part_b = ar.take<double>((size_t)d.n_blocks * D);
+  float* rz = ar.take<float>(D);
+  float* rz_new = ar.take<float>(D);
+  float* pap = ar.take<float>(D);
+  float* rr = ar.take<float>(D);
+  float* d_res = ar.take<float>(64);
+  if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "pcg: workspace too small");
+  int rc, it = 0;
+  float res = __builtin_nanf("");
+  if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) return rc;
+  if ((rc = pcg_reduce(part_a, d.n_blocks, D, rz, nullptr, nullptr, st))) return rc;
+  for (it = 1; it <= max_iters; ++it) {
+    if ((rc = pcg_spmm_dot(&d, g, chain, prm, mode, dt, gates, P, AP, part_a, st))) return rc;
+    if ((rc = pcg_reduce(part_a, d.n_blocks, D, pap, nullptr, nullptr, st))) return rc;
+    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, X, R, part_a, part_b, st)))
+      return rc;
+    if ((rc = pcg_reduce(part_a, d.n_blocks, D, rr, d_res, nullptr, st))) return rc;
+    if ((rc = pcg_reduce(part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st))) return rc;
+    OSC_CUDA(cudaMemcpyAsync(&res, d_res, sizeof(float), cudaMemcpyDeviceToHost, st));
+    OSC_CUDA(cudaStreamSynchronize(st));
+    if ((double)res <= tol) break;  // solver.py:29-31
+    if (it == max_iters) break;
+    if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st))) return rc;
+    float* t = rz;
+    rz = rz_new;
+    rz_new = t;
+  }
+  if (it > max_iters) it = max_iters;
+  if (h_iters) *h_iters = it;
+  if (h_res) *h_res = res;
+  return OSC_OK;
+}
+
 int pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, int mode,
               float dt, int warm, float inertia, int jacobi, double tol, int max_iters,
               const float* Y, const float* U, const float* psi, const float* gates, int D, float* X,
@@ -509,50 +610,34 @@ int pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t
   int rc = pcg_plan(&d, &need);
   if (rc) return rc;
   if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
+  if (h_iters) *h_iters = 0;
+  if (h_res) *h_res = __builtin_nanf("");
+  if (g->N == 0 || max_iters < 1) return OSC_OK;
   Arena ar(workspace, ws_bytes);
-  const size_t nd = (size_t)g->N * D;
-  float* R = ar.take<float>(nd);
-  float* P = ar.take<float>(nd);
-  float* AP = ar.take<float>(nd);
-  double* part_a = ar.take<double>((size_t)d.n_blocks * D);
-  double* part_b = ar.take<double>((size_t)d.n_blocks * D);
-  double* part_c = ar.take<double>((size_t)d.n_blocks * D);
-  float* rz = ar.take<float>(D);
-  float* rz_new = ar.take<float>(D);
-  float* pap = ar.take<float>(D);
-  float* rr = ar.take<float>(D);
-  float* d_res = ar.take<float>(64);
+  float* R = ar.take<float>((size_t)g->N * D);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
-  (void)part_c;
-  int it = 0;
-  float res = __builtin_nanf("");
-  if (g->N > 0 && max_iters >= 1) {
-    if ((rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, R, st))) return rc;
-    if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) return rc;
-    if ((rc = pcg_reduce(part_a, d.n_blocks, D, rz, nullptr, nullptr, st))) return rc;
-    for (it = 1; it <= max_iters; ++it) {
-      if ((rc = pcg_spmm_dot(&d, g, chain, prm, mode, dt, gates, P, AP, part_a, st))) return rc;
-      if ((rc = pcg_reduce(part_a, d.n_blocks, D, pap, nullptr, nullptr, st))) return rc;
-      if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, X, R, part_a, part_b, st)))
-        return rc;
-      if ((rc = pcg_reduce(part_a, d.n_blocks, D, rr, d_res, nullptr, st))) return rc;
-      if ((rc = pcg_reduce(part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st))) return rc;
-      OSC_CUDA(cudaMemcpyAsync(&res, d_res, sizeof(float), cudaMemcpyDeviceToHost, st));
-      OSC_CUDA(cudaStreamSynchronize(st));
-      if ((double)res <= tol) break;  // solver.py:29-31
-      if (it == max_iters) break;
-      if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st))) return rc;
-      float* t = rz;
-      rz = rz_new;
-      rz_new = t;
-    }
-    if (it > max_iters) it = max_iters;
-  } else if (g->N == 0) {
-    it = 0;
-  }
-  if (h_iters) *h_iters = it;
-  if (h_res) *h_res = res;
-  return OSC_OK;
+  if ((rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, R, st))) return rc;
+  return pcg_core(d, g, chain, prm, mode, dt, jacobi, tol, max_iters, gates, X, R, ar, h_iters, h_res, st);
+}
+
+// Same recurrences for an arbitrary right-hand side and start vector (used by the screened-diffusion
+// gate solve, preprocess/diffusion.py:132-150): X holds x0 on entry, B the right-hand side (clobbered).
+int pcg_solve_system(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, int mode,
+                     float dt, int jacobi, double tol, int max_iters, const float* gates, int D, float* X,
+                     float* B, int* h_iters, float* h_res, void* workspace, size_t ws_bytes,
+                     cudaStream_t st) {
+  OSC_REQUIRE(g != nullptr && prm != nullptr && X != nullptr && B != nullptr, "pcg_solve_system: NULL argument");
+  OSC_REQUIRE(g->batch == 1, "pcg_solve_system handles one lattice");
+  osc_pcg_dims_t d{g->N, 0, g->N, D, 0};
+  size_t need = 0;
+  int rc = pcg_plan(&d, &need);
+  if (rc) return rc;
+  if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "pcg_solve_system: workspace too small");
+  if (h_iters) *h_iters = 0;
+  if (h_res) *h_res = __builtin_nanf("");
+  if (g->N == 0 || max_iters < 1) return OSC_OK;
+  Arena ar(workspace, ws_bytes);
+  return pcg_core(d, g, chain, prm, mode, dt, jacobi, tol, max_iters, gates, X, B, ar, h_iters, h_res, st);
 }
 
 // deltaH = sum_c diff_c . (M diff)_c   (receipts.py:21-25)
@@ -575,13 +660,16 @@ int delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* 
   float* Md = ar.take<float>(nd);
   double* part = ar.take<double>((size_t)d.n_blocks * D);
   float* colsum = ar.take<float>(D);
+  double* col64 = ar.take<double>(D);
   double* total = ar.take<double>(8);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "delta_h: workspace too small");
   diff_kernel<<<ew_grid((int64_t)nd), 256, 0, st>>>(U, Ustar, diff, (int64_t)nd);
   OSC_LAUNCH_CHECK("diff_kernel");
   if ((rc = pcg_spmm_dot(&d, g, chain, prm, OSC_MODE_STATIONARY, 0.f, gates, diff, Md, part, st)))
     return rc;
-  if ((rc = pcg_reduce(part, d.n_blocks, D, colsum, nullptr, total, st))) return rc;
+  if ((rc = pcg_reduce(part, d.n_blocks, D, colsum, nullptr, col64, st))) return rc;
+  sum_doubles_kernel<<<1, 1024, 0, st>>>(col64, D, total);
+  OSC_LAUNCH_CHECK("sum_doubles_kernel");
   OSC_CUDA(cudaMemcpyAsync(h_out, total, sizeof(double), cudaMemcpyDeviceToHost, st));
   OSC_CUDA(cudaStreamSynchronize(st));
   return OSC_OK;
