@@ -34,6 +34,7 @@ namespace osc {
 constexpr int SC = 4;  // columns per slab (one float4 per row)
 constexpr int PK_MAXK = 16;
 constexpr int RED_F4 = 32;  // float4 slots per reduction array (>= warps per CTA)
+constexpr int SCR_CTAS_PER_SM = 8;  // scratch rows are provisioned for this many resident CTAs per SM
 
 struct BatchedK {
   const float* Y;
@@ -46,6 +47,8 @@ struct BatchedK {
   int2* rec;                     // [batch][2][G] {iterations, float bits of max_c ||r_c||^2}
   const int4* fix_list;          // list mode: {lattice, slab, forced settle its, forced U* its}
   const int* fix_count;
+  float4* scratch;               // [gridDim.x][2][N]: gather sums of Y (shared by the two initial
+                                 // residuals) and (U_in - U - r_settle)/dt for the deltaH identity
   const unsigned short* pk_nbr;  // packed graph image [batch][kq][N] ushort4 (byte offsets j*16)
   const float* pk_w;             // [batch][kq][N] float4
   int64_t batch, n_work;
@@ -138,10 +141,10 @@ struct Slab {
   float4 X[TPT], R[TPT], AP[TPT];
 };
 
-// A(p) for one row: diag*p_own - offc * sum_t W_t p[nbr_t]; graph image is slot-major [c][row]
+// sum_t W_t p[nbr_t] for one row; graph image is slot-major [c][row]
 template <int KQ>
-__device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
-                                            int row, int N, int kq_rt, float diag, float offc) {
+__device__ __forceinline__ float4 gather_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
+                                             int row, int N, int kq_rt) {
   float4 acc = f4_zero();
   const int kq = KQ > 0 ? KQ : kq_rt;
   const char* pb = reinterpret_cast<const char*>(p_s);
@@ -154,9 +157,17 @@ __device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nb
     acc = f4_fma(ww.z, *reinterpret_cast<const float4*>(pb + jj.z), acc);
     acc = f4_fma(ww.w, *reinterpret_cast<const float4*>(pb + jj.w), acc);
   }
-  const float4 own = p_s[row];
+  return acc;
+}
+__device__ __forceinline__ float4 combine_row(float4 own, float4 acc, float diag, float offc) {
   return make_float4(diag * own.x - offc * acc.x, diag * own.y - offc * acc.y,
                      diag * own.z - offc * acc.z, diag * own.w - offc * acc.w);
+}
+// A(p) for one row: diag*p_own - offc * sum_t W_t p[nbr_t]
+template <int KQ>
+__device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
+                                            int row, int N, int kq_rt, float diag, float offc) {
+  return combine_row(p_s[row], gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq_rt), diag, offc);
 }
 
 // One PCG solve for this CTA's slab (solver.py:15-37).  On exit st.X holds the iterate of the
@@ -165,15 +176,21 @@ __device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nb
 template <int TPT, int KQ>
 __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max_iters, int forced,
                           int N, int kq, float4* p_s, const float* diag_s, const float* im_s, const ushort4* nbr_s,
-                          const float4* w_s, float4* red, const bool (&act)[TPT], float* rr_out) {
+                          const float4* w_s, float4* red, const bool (&act)[TPT], float* rr_out,
+                          float4* acc_out, const float4* acc_in) {
+  // acc_out != nullptr: the gather sums of x0 are written there (thread-private rows);
+  // acc_in  != nullptr: they are read back instead of gathering x0 again (same x0, same graph:
+  //                     bit-identical to recomputing them).
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nw = T >> 5;
   float4* redA = red;               // init r.z, then p.Ap
   float4* redB = red + RED_F4;      // r.r
   float4* redC = red + 2 * RED_F4;  // r.z'
+  if (acc_in == nullptr) {
 #pragma unroll
-  for (int m = 0; m < TPT; ++m)
-    if (act[m]) p_s[tid + T * m] = st.X[m];
+    for (int m = 0; m < TPT; ++m)
+      if (act[m]) p_s[tid + T * m] = st.X[m];
+  }
   __syncthreads();  // x0 visible; diag_s, im_s of this solve visible
   // ---- r0 = b - A x0 ; z0 ; rz
   float4 z0[TPT];
@@ -184,7 +201,14 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     if (act[m]) {
       const int row = tid + T * m;
       const float imr = im_s[row];
-      const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, diag_s[row], c.offc);
+      float4 g;
+      if (acc_in != nullptr) {
+        g = acc_in[row];
+      } else {
+        g = gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq);
+        if (acc_out != nullptr) acc_out[row] = g;
+      }
+      const float4 a = combine_row(st.X[m], g, diag_s[row], c.offc);
       float4 r = st.R[m];
       r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
       st.R[m] = r;
@@ -380,6 +404,13 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
 #pragma unroll
   for (int m = 0; m < TPT; ++m) act[m] = (tid + T * m) < N;
 
+  // x0 = Y for both solves when the caller gave no U_in: one gather pass over Y serves both initial
+  // residuals.  With settle + U* + deltaH in one call, M(U - U*) follows from the two final
+  // residuals (see below) and the deltaH SpMM disappears as well: 12 -> 10 SpMMs per lattice.
+  const bool share_r0 = P.do_settle && P.do_ustar && P.U_in == nullptr;
+  const bool dh_fast = P.do_settle && P.do_ustar && P.do_dh;
+  float4* scr_acc = P.scratch + (size_t)blockIdx.x * 2 * N;
+  float4* scr_t1 = scr_acc + N;
   const bool list_mode = P.fix_list != nullptr;
   const int64_t n_work = list_mode ? (int64_t)(*P.fix_count) : P.n_work;
   for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
@@ -449,11 +480,26 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           }
         }
         const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, N, kq, p_s,
-                                              diag_s, im_s, nbr_s, w_s, red, act, &rr);
+                                              diag_s, im_s, nbr_s, w_s, red, act, &rr,
+                                              share_r0 ? scr_acc : nullptr, nullptr);
         if (Uo != nullptr) {
 #pragma unroll
           for (int m = 0; m < TPT; ++m)
             if (act[m]) *reinterpret_cast<float4*>(Uo + (int64_t)(tid + T * m) * P.D + col) = st.X[m];
+        }
+        if (dh_fast) {
+          // (I + dt M) U = b - r_s with b = U_in + dt RHS  =>  M U = RHS + (U_in - U - r_s)/dt
+          const float idt = __fdiv_rn(1.0f, P.dt);
+#pragma unroll
+          for (int m = 0; m < TPT; ++m) {
+            if (act[m]) {
+              const int row = tid + T * m;
+              const float4 u0 = *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col);
+              const float4 x = st.X[m], r = st.R[m];
+              scr_t1[row] = make_float4(((u0.x - x.x) - r.x) * idt, ((u0.y - x.y) - r.y) * idt,
+                                        ((u0.z - x.z) - r.z) * idt, ((u0.w - x.w) - r.w) * idt);
+            }
+          }
         }
         if (tid == 0) P.rec[(b * 2 + 0) * P.G + s] = make_int2(iters, __float_as_int(rr));
       }
@@ -487,7 +533,8 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           }
         }
         const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, N, kq, p_s,
-                                              diag_s, im_s, nbr_s, w_s, red, act, &rr);
+                                              diag_s, im_s, nbr_s, w_s, red, act, &rr, nullptr,
+                                              share_r0 ? scr_acc : nullptr);
         if (P.Ustar_out != nullptr) {
           float* So = P.Ustar_out + b * (int64_t)N * P.D;
 #pragma unroll
@@ -496,7 +543,31 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         }
         if (tid == 0) P.rec[(b * 2 + 1) * P.G + s] = make_int2(iters, __float_as_int(rr));
         // ---------------- deltaH = <U - U*, M (U - U*)>
-        if (P.do_dh) {
+        if (dh_fast) {
+          // M U* = RHS - r_u  =>  M (U - U*) = (U_in - U - r_s)/dt + r_u : no SpMM, thread-local.
+          // (The recurrence residuals differ from the true ones by ~eps*||A||*|U|, the same size as
+          //  the rounding of a fresh fp32 matvec on U - U*.)
+          float4 part = f4_zero();
+#pragma unroll
+          for (int m = 0; m < TPT; ++m) {
+            if (act[m]) {
+              const int row = tid + T * m;
+              const float4 u = *reinterpret_cast<const float4*>(Uo + (int64_t)row * P.D + col);
+              const float4 t1 = scr_t1[row];
+              const float4 x = st.X[m], r = st.R[m];
+              const float4 d = make_float4(__fsub_rn(u.x, x.x), __fsub_rn(u.y, x.y), __fsub_rn(u.z, x.z),
+                                           __fsub_rn(u.w, x.w));
+              part = f4_add(part, f4_mul(d, f4_add(t1, r)));
+            }
+          }
+          __syncthreads();  // the solve's last readers of `red` are done
+          warp_reduce4(part, red + warp, lane);
+          __syncthreads();
+          if (warp == 0) {
+            const float4 tot = block_total(red, T >> 5, lane);
+            if (lane == 0) P.dh_part[b * P.G + s] = (double)((tot.x + tot.y) + (tot.z + tot.w));
+          }
+        } else if (P.do_dh) {
 #pragma unroll
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
@@ -614,7 +685,8 @@ int batched_workspace(int64_t batch, int64_t N, int D, size_t* bytes) {
   *bytes = align_up((size_t)batch * 2 * G * sizeof(int2)) + align_up((size_t)batch * G * sizeof(double)) +
            align_up((size_t)batch * G * sizeof(int4)) + align_up(sizeof(int)) +
            align_up((size_t)batch * N * PK_MAXK * sizeof(unsigned short)) +
-           align_up((size_t)batch * N * PK_MAXK * sizeof(float)) + 1024;
+           align_up((size_t)batch * N * PK_MAXK * sizeof(float)) +
+           align_up((size_t)SCR_CTAS_PER_SM * sm_count() * 2 * N * sizeof(float4)) + 1024;
   return OSC_OK;
 }
 
@@ -656,6 +728,7 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   int* fix_count = ar.take<int>(1);
   unsigned short* pn = ar.take<unsigned short>((size_t)g->batch * N * kp);
   float* pw = ar.take<float>((size_t)g->batch * N * kp);
+  float4* scratch = ar.take<float4>((size_t)SCR_CTAS_PER_SM * sm_count() * 2 * N);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "batched_settle: workspace too small");
   OSC_CUDA(cudaMemsetAsync(fix_count, 0, sizeof(int), st));
   {
@@ -671,6 +744,7 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   P.dh_part = dh_part; P.rec = rec;
   P.fix_list = nullptr; P.fix_count = nullptr;
   P.pk_nbr = pn; P.pk_w = pw;
+  P.scratch = scratch;
   P.batch = g->batch; P.N = N; P.kq = kq; P.D = a->D; P.G = G;
   P.CH = 2;
   {
@@ -697,6 +771,7 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   int occ = 0;
   OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, threads, smem));
   if (occ < 1) return fail(OSC_ERR_UNSUPPORTED, "batched_settle: kernel does not fit on an SM");
+  if (occ > SCR_CTAS_PER_SM) occ = SCR_CTAS_PER_SM;
   const int64_t resident = (int64_t)occ * sm_count();
   const unsigned grid = (unsigned)(P.n_work < resident ? P.n_work : resident);
   fn<<<grid, threads, smem, st>>>(P);
