@@ -286,6 +286,19 @@ def run_ours(args) -> None:
         peak = float(peaks["hbm_gbs"])
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src}
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (per lattice,
+    # scaled to this launch); profiles/ncu_traffic.json names the capture it came from
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(dom)
+        if tr:
+            roof["traffic"] = tr["dram_bytes_per_lattice"] * B
+            roof["traffic_source"] = tr["source"]
+    except Exception:
+        pass
+    if dom == "batched_settle":
+        roof["note"] = ("everything but Y in / U out stays on chip, so HBM is not the binding resource: ncu shows "
+                        "LDS-latency (short scoreboard) stalls, shared-memory pipe 58 % busy -- profiles/README.md")
     roof["kernel_ms_per_step"] = kern_ms
     roof["share_of_step"] = {k: v / (ms / args.steps) for k, v in kern_ms.items()}
 
@@ -307,7 +320,8 @@ def run_ours(args) -> None:
                     "h2d_bytes_per_step": int(Y_host.numel() * 4 + psi_host.numel() * 4),
                     "d2h_bytes_per_step": int(res_host.numel() * 8)},
             # normalize, knn_tc, rescore, assemble(3 kernels), pack, settle, resolve, settle(fix), finalize
-            "gpu_launches": 11 * args.steps,
+            # normalize, knn_tc2, rescore, exact_rows, assemble x3, pack, settle, resolve, settle(fix), finalize
+            "gpu_launches": 12 * args.steps,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": workers, "kind": "port",
@@ -315,6 +329,16 @@ def run_ours(args) -> None:
                                        f"{workers} processes x 1 BLAS thread"},
             "check": check,
         }
+    if not args.no_large and world == 1:
+        # the second half of BASELINE.json's metric (ms/settle of ONE big lattice) at the size that
+        # builds in seconds; N=10M and the multi-GPU runs (--workload large) are under profiles/
+        del Y, Y_host
+        torch.cuda.empty_cache()
+        big = measure_large(args.N, args.D, args.k, steps=2, warmup=1, partition="rows", world=1, rank=0,
+                            local=local)
+        line["large_lattice"] = {k: big[k] for k in ("metric", "value", "unit", "n_gpus", "config", "roofline",
+                                                     "build_ms", "receipt_light_ms", "check")}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -322,25 +346,21 @@ def run_ours(args) -> None:
 
 
 # ----------------------------------------------------------------------------- large single lattice
-def run_large(args) -> None:
+def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", world=1, rank=0, local=0):
     """BASELINE.json configs[3]/[4]: ONE big lattice (N up to 10M), kNN build + PCG settle, the rows
     (or column slabs) partitioned over the GPUs.  A step = one settle(12, 1e-3) from U = Y on the built
-    lattice (the metric's `ms/settle`); build, U* + deltaH and the per-kernel rooflines ride along."""
-    import numpy as np
+    lattice (the metric's `ms/settle`); build, U* + deltaH and the per-kernel rooflines ride along.
+    Returns the JSON-able result dict on rank 0 (None elsewhere)."""
+    import types
+
     import torch
     import torch.distributed as dist
 
     from oscillink_b200 import _cabi
     from oscillink_b200.sharded_api import ShardedLattice, _NativeKernels, gather_rows, shard_bounds
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N, D, k = args.N, args.D, args.k
+    args = types.SimpleNamespace(steps=steps, warmup=warmup, chain_len=chain_len, partition=partition)
     row0, n_local, _ = shard_bounds(N, world, rank)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -460,6 +480,7 @@ def run_large(args) -> None:
             "whole_settle": {"algorithmic_bytes": solve_bytes, "achieved_gbs": solve_bytes / (ms_settle / 1e3) / 1e9,
                              "frac": solve_bytes / (ms_settle / 1e3) / 1e9 / peak},
             "bytes_per_iteration": iter_bytes}
+    line = None
     if rank == 0:
         line = {
             "metric": f"ms/settle at N={N},D={D}", "value": ms_settle, "unit": "ms", "n_gpus": world,
@@ -478,8 +499,27 @@ def run_large(args) -> None:
             "build_ms": build_ms, "receipt_light_ms": receipt_ms,
             "check": {"iters": iters, "res": float(st["res"]), "ustar_iters": rec["meta"]["ustar_iters"],
                       "ustar_res": rec["meta"]["ustar_res"], "deltaH": rec["deltaH_total"],
-                      "avg_degree": rec["meta"]["avg_degree"], "nnz": nnz},
+                      "avg_degree": rec["meta"]["avg_degree"], "nnz": nnz,
+                      "rows_recomputed_exhaustively": int(getattr(lat, "n_exhaustive", torch.zeros(1)).item())},
         }
+    del lat, kf, X
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_large(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_large(args.N, args.D, args.k, steps=args.steps, warmup=args.warmup, chain_len=args.chain_len,
+                         partition=args.partition, world=world, rank=rank, local=local)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -501,6 +541,8 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--chain-len", type=int, default=0)
     ap.add_argument("--partition", default="rows", choices=["rows", "columns"])
+    ap.add_argument("--no-large", action="store_true",
+                    help="serving workload only: skip the one-big-lattice block of the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -120,6 +120,21 @@ int osc_knn_rescore(const float* Yn_q, const float* Yn_all, int64_t batch, int64
                     int32_t D, const int32_t* cand_idx, int32_t kc, int32_t k, int32_t* top_idx,
                     float* top_sim, float* gap, void* stream);
 
+/* Checked re-scoring: as osc_knn_rescore, plus a completeness test of every row's candidate list.
+ * A column outside the list scored <= a_min (smallest approximate score kept) in the approximate
+ * pass, so it can only be a true top-k column if a_min + eps >= the exact k-th score; such rows are
+ * recomputed exhaustively (all N columns, same fp64-accumulated dot, graph.py:46-52 ordering).
+ * eps bounds |approximate - exact| of the candidate engine (OSC_KNN_EPS covers 3xTF32 with
+ * truncating accumulation and the fp32 FMA engine).  *d_n_flagged (device int32) receives the
+ * number of rows that took the exhaustive path.  row0 = global id of the first query row. */
+#define OSC_KNN_EPS 1e-5f
+int osc_knn_rescore_workspace(int64_t batch, int64_t n_rows, size_t* h_bytes);
+int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
+                            int64_t row0, int64_t N, int32_t D, const int32_t* cand_idx,
+                            const float* cand_sim, int32_t kc, int32_t k, float eps, int32_t* top_idx,
+                            float* top_sim, float* gap, int32_t* d_n_flagged, void* workspace,
+                            size_t ws_bytes, void* stream);
+
 /* K1b -- graph.py:50-52 (S>0 filter), :64-65 (mutual), :77-83 (row cap), :87-92 (degree,
  * normalised weights).  top_idx/top_sim are the directed lists of ALL N rows of each lattice.
  * scratch: N*batch floats.  nnz: [batch] int64 (device). */

@@ -18,6 +18,7 @@ _lib = None
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 KNN_AUTO, KNN_SIMT, KNN_TC = 0, 1, 2
 MODE_SETTLE, MODE_STATIONARY = 0, 1
+KNN_EPS = 1e-5  # OSC_KNN_EPS
 
 c_i32, c_i64, c_f32, c_f64, c_void_p, c_size_t = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_size_t
 
@@ -62,6 +63,10 @@ PROTOTYPES = {
     "osc_knn_candidates_workspace": (C.c_int, [c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, P(c_size_t)]),
     "osc_knn_rescore": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_void_p, c_i32, c_i32,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osc_knn_rescore_workspace": (C.c_int, [c_i64, c_i64, P(c_size_t)]),
+    "osc_knn_rescore_checked": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i32, c_void_p,
+                                          c_void_p, c_i32, c_i32, c_f32, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "osc_graph_assemble": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_f32, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osc_knn_build_workspace": (C.c_int, [c_i64, c_i64, c_i32, c_i32, c_i32, P(c_size_t)]),

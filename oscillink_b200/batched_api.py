@@ -119,9 +119,16 @@ class BatchedLattices:
         phase("knn_candidates", lambda: lib.osc_knn_candidates(
             Yn.data_ptr(), Yn.data_ptr(), P(hi), P(lo), P(hi), P(lo), B, N, 0, N, D, kc,
             _cabi.KNN_TC if use_tc else _cabi.KNN_SIMT, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st))
-        phase("knn_rescore", lambda: lib.osc_knn_rescore(
-            Yn.data_ptr(), Yn.data_ptr(), B, N, N, D, cand_idx.data_ptr(), kc, k, top_idx.data_ptr(),
-            top_sim.data_ptr(), self.gap.data_ptr(), st))
+        # canonical re-scoring + completeness check of every candidate list (rows that cannot be proven
+        # complete are recomputed exhaustively on device; n_exhaustive counts them)
+        self.n_exhaustive = torch.zeros(1, dtype=torch.int32, device=dev)
+        need = C.c_size_t(0)
+        _cabi.check(lib.osc_knn_rescore_workspace(B, N, C.byref(need)))
+        rws = self._workspace(need.value)
+        phase("knn_rescore", lambda: lib.osc_knn_rescore_checked(
+            Yn.data_ptr(), Yn.data_ptr(), B, N, 0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
+            _cabi.KNN_EPS, top_idx.data_ptr(), top_sim.data_ptr(), self.gap.data_ptr(),
+            self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st))
         phase("graph_assemble", lambda: lib.osc_graph_assemble(
             top_idx.data_ptr(), top_sim.data_ptr(), B, N, k, self.row_cap_val, self.nbr.data_ptr(),
             self.A.data_ptr(), self.W.data_ptr(), self.deg.data_ptr(), self.sqrt_deg.data_ptr(),

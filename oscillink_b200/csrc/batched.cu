@@ -61,6 +61,7 @@ struct BatchedK {
 
 struct SolveCoef {
   float diag0, diag1;  // operator diagonal = diag0 + diag1 * b_i
+  float diag_u, im_u;  // the same diagonal and 1/(Mdiag + 1e-12) for b_i == 1 (no gates given)
   float offc;
   float lamG, lamQ, dt;
   int settle;
@@ -136,6 +137,23 @@ __device__ __forceinline__ float4 block_total(const float4* red, int nw, int lan
                      __shfl_sync(0xffffffffu, t, 2), __shfl_sync(0xffffffffu, t, 3));
 }
 
+// Component-local variant: lane l gets the total of component l&3 only (no broadcast).  The CG scalars
+// (rz, p.Ap, r.z') are per column, so each lane divides for ITS column and bcast4 hands the four
+// quotients to everybody: one division per lane instead of four, same values as before.
+__device__ __forceinline__ float block_total_c(const float4* red, int nw, int lane) {
+  const float* rf = reinterpret_cast<const float*>(red);
+  float t = 0.f;
+  for (int i = lane; i < nw * 4; i += 32) t += rf[i];
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t;
+}
+__device__ __forceinline__ float4 bcast4(float q) {
+  return make_float4(__shfl_sync(0xffffffffu, q, 0), __shfl_sync(0xffffffffu, q, 1),
+                     __shfl_sync(0xffffffffu, q, 2), __shfl_sync(0xffffffffu, q, 3));
+}
+
 template <int TPT>
 struct Slab {
   float4 X[TPT], R[TPT], AP[TPT];
@@ -200,7 +218,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     z0[m] = f4_zero();
     if (act[m]) {
       const int row = tid + T * m;
-      const float imr = im_s[row];
+      const float imr = im_s ? im_s[row] : c.im_u;
       float4 g;
       if (acc_in != nullptr) {
         g = acc_in[row];
@@ -208,7 +226,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
         g = gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq);
         if (acc_out != nullptr) acc_out[row] = g;
       }
-      const float4 a = combine_row(st.X[m], g, diag_s[row], c.offc);
+      const float4 a = combine_row(st.X[m], g, diag_s ? diag_s[row] : c.diag_u, c.offc);
       float4 r = st.R[m];
       r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
       st.R[m] = r;
@@ -218,7 +236,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   }
   warp_reduce4(part, redA + warp, lane);
   __syncthreads();  // also: every gather of x0 has completed
-  float4 rz = block_total(redA, nw, lane);
+  float rz = block_total_c(redA, nw, lane);  // component lane&3
 #pragma unroll
   for (int m = 0; m < TPT; ++m)
     if (act[m]) p_s[tid + T * m] = z0[m];
@@ -233,15 +251,16 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     for (int m = 0; m < TPT; ++m) {
       if (act[m]) {
         const int row = tid + T * m;
-        st.AP[m] = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, diag_s[row], c.offc);
-        part = f4_add(part, f4_mul(p_s[row], st.AP[m]));
+        const float4 own = p_s[row];
+        st.AP[m] = combine_row(own, gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq),
+                               diag_s ? diag_s[row] : c.diag_u, c.offc);
+        part = f4_add(part, f4_mul(own, st.AP[m]));
       }
     }
     warp_reduce4(part, redA + warp, lane);
     __syncthreads();
-    const float4 pap = block_total(redA, nw, lane);
-    const float4 alpha = make_float4(__fdiv_rn(rz.x, pap.x + 1e-18f), __fdiv_rn(rz.y, pap.y + 1e-18f),
-                                     __fdiv_rn(rz.z, pap.z + 1e-18f), __fdiv_rn(rz.w, pap.w + 1e-18f));
+    const float pap = block_total_c(redA, nw, lane);
+    const float4 alpha = bcast4(__fdiv_rn(rz, pap + 1e-18f));
     // ---- C: x, r update; rr and rz'
     float4 prr = f4_zero(), prz = f4_zero();
     float4 zz[TPT];
@@ -259,7 +278,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
                         fmaf(-ap.w, alpha.w, r.w));
         st.X[m] = x;
         st.R[m] = r;
-        const float im = im_s[row];
+        const float im = im_s ? im_s[row] : c.im_u;
         const float4 z = make_float4(r.x * im, r.y * im, r.z * im, r.w * im);
         zz[m] = z;
         prr = f4_add(prr, f4_mul(r, r));
@@ -268,16 +287,16 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     }
     warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
     __syncthreads();
-    const float4 rr = block_total(redB, nw, lane);
-    const float4 rzn = block_total(redC, nw, lane);
-    mx = fmaxf(fmaxf(rr.x, rr.y), fmaxf(rr.z, rr.w));
+    const float rr = block_total_c(redB, nw, lane);
+    const float rzn = block_total_c(redC, nw, lane);
+    mx = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     // identical in every thread (same summation order) -> uniform branch
     const bool stop = forced > 0 ? (it >= forced)
                                  : ((double)__fsqrt_rn(mx) <= tol || it >= max_iters);
     if (stop) break;
     // ---- E: p = z + beta p
-    const float4 beta = make_float4(__fdiv_rn(rzn.x, rz.x + 1e-18f), __fdiv_rn(rzn.y, rz.y + 1e-18f),
-                                    __fdiv_rn(rzn.z, rz.z + 1e-18f), __fdiv_rn(rzn.w, rz.w + 1e-18f));
+    const float4 beta = bcast4(__fdiv_rn(rzn, rz + 1e-18f));
     rz = rzn;
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
@@ -455,11 +474,15 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         c.diag0 = 1.0f + P.dt * (P.lamG + P.lamC);
         c.diag1 = P.dt * P.lamQ;
         c.offc = P.dt * P.lamC;
+        c.diag_u = c.diag0 + c.diag1 * 1.0f;
+        c.im_u = __fdiv_rn(1.0f, md_of(c, 1.0f) + 1e-12f);
         __syncthreads();  // previous solve's readers of diag_s, im_s, p_s are done
-        for (int e = tid; e < N; e += T) {
-          const float bq = gb ? gb[e] : 1.0f;
-          diag_s[e] = c.diag0 + c.diag1 * bq;
-          im_s[e] = __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f);
+        if (gb != nullptr) {
+          for (int e = tid; e < N; e += T) {
+            const float bq = gb[e];
+            diag_s[e] = c.diag0 + c.diag1 * bq;
+            im_s[e] = __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f);
+          }
         }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
@@ -480,8 +503,8 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           }
         }
         const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, N, kq, p_s,
-                                              diag_s, im_s, nbr_s, w_s, red, act, &rr,
-                                              share_r0 ? scr_acc : nullptr, nullptr);
+                                              gb ? diag_s : nullptr, gb ? im_s : nullptr, nbr_s, w_s, red,
+                                              act, &rr, share_r0 ? scr_acc : nullptr, nullptr);
         if (Uo != nullptr) {
 #pragma unroll
           for (int m = 0; m < TPT; ++m)
@@ -511,11 +534,15 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         c.diag0 = P.lamG + P.lamC;
         c.diag1 = P.lamQ;
         c.offc = P.lamC;
+        c.diag_u = c.diag0 + c.diag1 * 1.0f;
+        c.im_u = __fdiv_rn(1.0f, md_of(c, 1.0f) + 1e-12f);
         __syncthreads();  // the settle solve's readers of diag_s, im_s are done
-        for (int e = tid; e < N; e += T) {
-          const float bq = gb ? gb[e] : 1.0f;
-          diag_s[e] = c.diag0 + c.diag1 * bq;
-          im_s[e] = __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f);
+        if (gb != nullptr) {
+          for (int e = tid; e < N; e += T) {
+            const float bq = gb[e];
+            diag_s[e] = c.diag0 + c.diag1 * bq;
+            im_s[e] = __fdiv_rn(1.0f, md_of(c, bq) + 1e-12f);
+          }
         }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
@@ -533,8 +560,8 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           }
         }
         const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, N, kq, p_s,
-                                              diag_s, im_s, nbr_s, w_s, red, act, &rr, nullptr,
-                                              share_r0 ? scr_acc : nullptr);
+                                              gb ? diag_s : nullptr, gb ? im_s : nullptr, nbr_s, w_s, red,
+                                              act, &rr, nullptr, share_r0 ? scr_acc : nullptr);
         if (P.Ustar_out != nullptr) {
           float* So = P.Ustar_out + b * (int64_t)N * P.D;
 #pragma unroll
@@ -586,7 +613,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
               const int row = tid + T * m;
-              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, diag_s[row], c.offc);
+              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, gb ? diag_s[row] : c.diag_u, c.offc);
               part = f4_add(part, f4_mul(p_s[row], a));
             }
           }

@@ -42,8 +42,8 @@ int knn_tc_supported(int64_t N, int D, int kc);
 int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
                   int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
                   int32_t* cand_idx, float* cand_sim, cudaStream_t st);
-int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int, int,
-                   int32_t*, float*, float*, cudaStream_t);
+int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, const int32_t*,
+                   const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t);
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
                     int32_t*, float*, int64_t*, float*, cudaStream_t);
 int pcg_plan(osc_pcg_dims_t*, size_t*);
@@ -161,7 +161,33 @@ int osc_knn_rescore(const float* Yn_q, const float* Yn_all, int64_t batch, int64
   cudaStream_t st = (cudaStream_t)stream;
   OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * batch * n_rows * k, st));
   OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * batch * n_rows * k, st));
-  return launch_rescore(Yn_q, Yn_all, batch, n_rows, N, D, cand_idx, kc, k, top_idx, top_sim, gap, st);
+  return launch_rescore(Yn_q, Yn_all, batch, n_rows, 0, N, D, cand_idx, nullptr, kc, k, 0.f, top_idx, top_sim,
+                        gap, nullptr, nullptr, st);
+}
+
+int osc_knn_rescore_workspace(int64_t batch, int64_t n_rows, size_t* h_bytes) {
+  OSC_REQUIRE(h_bytes != nullptr && batch >= 0 && n_rows >= 0, "knn_rescore_workspace: bad argument");
+  *h_bytes = align_up((size_t)batch * n_rows * sizeof(int64_t)) + 256;
+  return OSC_OK;
+}
+
+int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
+                            int64_t row0, int64_t N, int32_t D, const int32_t* cand_idx,
+                            const float* cand_sim, int32_t kc, int32_t k, float eps, int32_t* top_idx,
+                            float* top_sim, float* gap, int32_t* d_n_flagged, void* workspace,
+                            size_t ws_bytes, void* stream) {
+  OSC_REQUIRE(Yn_q && Yn_all && cand_idx && cand_sim && top_idx && top_sim && d_n_flagged,
+              "knn_rescore_checked: NULL argument");
+  OSC_REQUIRE(k >= 1 && kc >= k && batch <= 65535 && eps >= 0.f, "knn_rescore_checked: need 1 <= k <= kc");
+  if (batch == 0 || n_rows == 0) return OSC_OK;
+  size_t need = 0;
+  osc_knn_rescore_workspace(batch, n_rows, &need);
+  if (ws_bytes < need || workspace == nullptr) return fail(OSC_ERR_WORKSPACE, "knn_rescore_checked: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * batch * n_rows * k, st));
+  OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * batch * n_rows * k, st));
+  return launch_rescore(Yn_q, Yn_all, batch, n_rows, row0, N, D, cand_idx, cand_sim, kc, k, eps, top_idx,
+                        top_sim, gap, static_cast<int64_t*>(workspace), d_n_flagged, st);
 }
 
 int osc_graph_assemble(const int32_t* top_idx, const float* top_sim, int64_t batch, int64_t N, int32_t k,
@@ -189,6 +215,7 @@ int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int3
   b += align_up(rows * kc * sizeof(int32_t)) + align_up(rows * kc * sizeof(float));  // candidates
   b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
   b += align_up(rows * sizeof(float));                                               // cap scale
+  b += align_up(rows * sizeof(int64_t)) + 512;                                       // flagged rows + counter
   *h_bytes = b + 1024;
   return OSC_OK;
 }
@@ -235,12 +262,17 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   int32_t* top_idx = ar.take<int32_t>(rows * k);
   float* top_sim = ar.take<float>(rows * k);
   float* cscale = ar.take<float>(rows);
+  int64_t* flagged = ar.take<int64_t>(rows);
+  int* n_flagged = ar.take<int>(1);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
   if ((rc = launch_normalize(Y, (int64_t)rows, D, Yn, hi, lo, st))) return rc;
   if ((rc = osc_knn_candidates(Yn, Yn, hi, lo, hi, lo, batch, N, 0, N, D, kc, eng, cand_idx, cand_sim,
                                nullptr, 0, stream)))
     return rc;
-  if ((rc = osc_knn_rescore(Yn, Yn, batch, N, N, D, cand_idx, kc, k, top_idx, top_sim, gap, stream)))
+  OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * rows * k, st));
+  OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * rows * k, st));
+  if ((rc = launch_rescore(Yn, Yn, batch, N, 0, N, D, cand_idx, cand_sim, kc, k, OSC_KNN_EPS, top_idx, top_sim,
+                           gap, flagged, n_flagged, st)))
     return rc;
   return launch_assemble(top_idx, top_sim, batch, N, k, row_cap, nbr, A, W, deg, sqrt_deg, nnz, cscale, st);
 }

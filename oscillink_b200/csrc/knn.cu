@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256)
 knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, int64_t n_rows,
                    int64_t N, int D, const int32_t* __restrict__ cand_idx, int kc, int k,
                    int32_t* __restrict__ top_idx, float* __restrict__ top_sim,
-                   float* __restrict__ gap) {
+                   float* __restrict__ gap, const float* __restrict__ cand_sim, float eps,
+                   int64_t* __restrict__ flagged, int* __restrict__ n_flagged) {
   extern __shared__ float smem[];
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,14 +198,106 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
     if (rank == k - 1) kth = s;
     if (rank == k) nxt = s;
   }
-  if (gap != nullptr) {
-    // exactly one lane holds each of kth / nxt
+  // exactly one lane holds each of kth / nxt
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
-      nxt = fmaxf(nxt, __shfl_xor_sync(0xffffffffu, nxt, off));
+  for (int off = 16; off > 0; off >>= 1) {
+    kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
+    nxt = fmaxf(nxt, __shfl_xor_sync(0xffffffffu, nxt, off));
+  }
+  if (gap != nullptr && lane == 0) gap[b * n_rows + r] = (nxt == -INFINITY) ? INFINITY : kth - nxt;
+  // ---- completeness check of the candidate list.  Every column outside the list scored at most
+  // a_min (the smallest APPROXIMATE score in the list) in the approximate pass, i.e. at most
+  // a_min + eps exactly; it can only belong to the true top-k if that reaches the exact k-th
+  // score.  Such rows (and rows with fewer than k valid candidates) are re-done exhaustively.
+  if (cand_sim != nullptr && flagged != nullptr && (int64_t)kc < N - 1) {
+    const float* cs = cand_sim + (b * n_rows + r) * kc;
+    float amin = INFINITY;
+    for (int c = lane; c < kc; c += 32)
+      if (sj[c] >= 0) amin = fminf(amin, cs[c]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off));
+    // kth == +inf: fewer than k valid candidates
+    if (lane == 0 && (kth == INFINITY || amin + eps >= kth)) flagged[atomicAdd(n_flagged, 1)] = b * n_rows + r;
+  }
+}
+
+// ---------------------------------------------------------------- exhaustive fallback rows
+// One CTA per flagged row (grid-stride over the flagged list): every warp scans a strided subset of
+// the N columns with the same fp64-accumulated dot as the re-scoring pass and keeps its k+1 best in
+// shared memory; warp 0 merges the lists and writes the canonical top-k (+ gap).
+__global__ void __launch_bounds__(256)
+knn_exact_rows_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, int64_t n_rows,
+                      int64_t row0, int64_t N, int D, int k, const int64_t* __restrict__ flagged,
+                      const int* __restrict__ n_flagged, int32_t* __restrict__ top_idx,
+                      float* __restrict__ top_sim, float* __restrict__ gap) {
+  extern __shared__ float smem[];
+  const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = k + 1;
+  float* lv = smem + (size_t)w * L;
+  int* li = reinterpret_cast<int*>(smem + (size_t)warps * L) + (size_t)w * L;
+  int* head = reinterpret_cast<int*>(smem + (size_t)2 * warps * L);  // merge cursors [warps]
+  const int total = *n_flagged;
+  for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    const int64_t gid = flagged[f];
+    const int64_t b = gid / n_rows, r = gid - b * n_rows;
+    const int64_t self = row0 + r;
+    const float* yi = Yq + gid * D;
+    const float* all = Yall + b * N * D;
+    int cnt = 0;
+    for (int64_t j = w; j < N; j += warps) {
+      if (j == self) continue;
+      const float* yj = all + j * D;
+      double acc = 0.0;
+      for (int d = lane; d < D; d += 32) acc = fma((double)yi[d], (double)yj[d], acc);
+      acc = warp_sum(acc);
+      const float sc = (float)acc;
+      if (lane == 0 && (cnt < L || better(sc, (int)j, lv[L - 1], li[L - 1]))) {
+        int p = (cnt < L) ? cnt : L - 1;
+        while (p > 0 && better(sc, (int)j, lv[p - 1], li[p - 1])) {
+          lv[p] = lv[p - 1];
+          li[p] = li[p - 1];
+          --p;
+        }
+        lv[p] = sc;
+        li[p] = (int)j;
+        if (cnt < L) ++cnt;
+      }
     }
-    if (lane == 0) gap[b * n_rows + r] = (nxt == -INFINITY) ? INFINITY : kth - nxt;
+    if (lane == 0) {
+      for (int c = cnt; c < L; ++c) {
+        lv[c] = -INFINITY;
+        li[c] = 0x7fffffff;
+      }
+      head[w] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float* av = smem;
+      const int* ai = reinterpret_cast<const int*>(smem + (size_t)warps * L);
+      const int64_t o = gid * k;
+      float kth = INFINITY, nxt = -INFINITY;
+      for (int rank = 0; rank < L; ++rank) {
+        int best = -1;
+        for (int q = 0; q < warps; ++q) {
+          if (head[q] >= L || ai[q * L + head[q]] == 0x7fffffff) continue;
+          if (best < 0 || better(av[q * L + head[q]], ai[q * L + head[q]], av[best * L + head[best]],
+                                 ai[best * L + head[best]]))
+            best = q;
+        }
+        if (best < 0) break;
+        const float sv = av[best * L + head[best]];
+        const int jv = ai[best * L + head[best]];
+        head[best]++;
+        if (rank < k) {
+          top_idx[o + rank] = jv;
+          top_sim[o + rank] = sv;
+        }
+        if (rank == k - 1) kth = sv;
+        if (rank == k) nxt = sv;
+      }
+      if (gap != nullptr) gap[gid] = (nxt == -INFINITY) ? INFINITY : kth - nxt;
+    }
+    __syncthreads();
   }
 }
 
@@ -234,15 +327,30 @@ int launch_knn_simt(const float* Yq, const float* Yall, int64_t batch, int64_t n
   return OSC_OK;
 }
 
-int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t N,
-                   int D, const int32_t* cand_idx, int kc, int k, int32_t* top_idx, float* top_sim,
-                   float* gap, cudaStream_t st) {
+// cand_sim / flagged / n_flagged may be NULL (no completeness check, the plain osc_knn_rescore).
+// With them: rows whose candidate list cannot be proven complete are recomputed exhaustively.
+int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t row0,
+                   int64_t N, int D, const int32_t* cand_idx, const float* cand_sim, int kc, int k,
+                   float eps, int32_t* top_idx, float* top_sim, float* gap, int64_t* flagged,
+                   int* n_flagged, cudaStream_t st) {
   const int warps = 8;
   const size_t smem = (size_t)warps * kc * (sizeof(float) + sizeof(int));
   dim3 grid((unsigned)((n_rows + warps - 1) / warps), (unsigned)batch);
-  knn_rescore_kernel<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k,
-                                                     top_idx, top_sim, gap);
+  const bool check = cand_sim != nullptr && flagged != nullptr && n_flagged != nullptr;
+  if (check) OSC_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(int), st));
+  knn_rescore_kernel<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k, top_idx,
+                                                     top_sim, gap, check ? cand_sim : nullptr, eps,
+                                                     check ? flagged : nullptr, n_flagged);
   OSC_LAUNCH_CHECK("knn_rescore_kernel");
+  if (check && (int64_t)kc < N - 1) {
+    const size_t sm2 = (size_t)warps * (k + 1) * (sizeof(float) + sizeof(int)) + warps * sizeof(int);
+    int64_t blocks = batch * n_rows;
+    const int64_t cap = 2 * (int64_t)sm_count();
+    if (blocks > cap) blocks = cap;
+    knn_exact_rows_kernel<<<(unsigned)blocks, warps * 32, sm2, st>>>(Yq, Yall, n_rows, row0, N, D, k, flagged,
+                                                                    n_flagged, top_idx, top_sim, gap);
+    OSC_LAUNCH_CHECK("knn_exact_rows_kernel");
+  }
   return OSC_OK;
 }
 

@@ -299,9 +299,15 @@ class ShardedLattice:
                     q(Yn), Yn.data_ptr(), q(hi), q(lo), P(hi), P(lo), 1, nl, r0, N, D, kc,
                     cabi.KNN_TC if use_tc else cabi.KNN_SIMT, cand_idx.data_ptr(), cand_sim.data_ptr(),
                     None, 0, st), "osc_knn_candidates")
-                cabi.check(lib.osc_knn_rescore(q(Yn), Yn.data_ptr(), 1, nl, N, D, cand_idx.data_ptr(), kc,
-                                               k, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
-                                               st), "osc_knn_rescore")
+                self.n_exhaustive = torch.zeros(1, dtype=torch.int32, device=dev)
+                need = C.c_size_t(0)
+                cabi.check(lib.osc_knn_rescore_workspace(1, nl, C.byref(need)))
+                rws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+                cabi.check(lib.osc_knn_rescore_checked(
+                    q(Yn), Yn.data_ptr(), 1, nl, r0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
+                    cabi.KNN_EPS, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
+                    self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st),
+                    "osc_knn_rescore_checked")
             self.gap_local = gap[:nl]
             top_idx_all = gather_rows(top_idx[:nl], N, self.group).contiguous()
             top_sim_all = gather_rows(top_sim[:nl], N, self.group).contiguous()

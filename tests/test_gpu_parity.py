@@ -341,3 +341,63 @@ def test_perf_snapshot_weakest_link(api):
     assert cr["verdict"] == ref["chain_verdict"]
     assert cr["weakest_link"]["edge"] == ref["weakest_link"]["edge"]
     assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < 1e-4
+
+
+# --------------------------------------------------------------------------- candidate-list completeness
+def test_exact_ties_beyond_the_candidate_margin_take_the_exhaustive_path(api):
+    """200 identical rows: every one of them has 199 columns tied at similarity 1.0, far more than the
+    k+4 candidates the approximate pass keeps.  graph.py:46-49 wants the k lowest indices among the
+    ties; the completeness check must notice the list cannot be proven complete and redo those rows."""
+    import torch
+
+    rs = np.random.RandomState(3)
+    base = rs.randn(400, 48).astype(np.float32)
+    Y = np.concatenate([base, np.repeat(base[:1], 200, axis=0)], axis=0)
+    Y = Y[rs.permutation(len(Y))]
+    o = SparseLattice(Y, k=6)
+    lat = api.OscillinkLattice(Y, kneighbors=6, deterministic_k=True)
+    assert np.array_equal(lat._nbr.cpu().numpy(), o.nbr.astype(np.int32))
+    np.testing.assert_allclose(lat._A.cpu().numpy(), o.A, rtol=2e-6, atol=1e-9)
+    bl = api.BatchedLattices(torch.from_numpy(Y[None]).cuda(), kneighbors=6)
+    assert int(bl.n_exhaustive.item()) >= 200
+    assert np.array_equal(bl.nbr[0].cpu().numpy(), o.nbr.astype(np.int32))
+
+
+def test_exhaustive_rows_equal_candidate_rows(api):
+    """eps = 10 forces EVERY row through knn_exact_rows_kernel; the tables must equal the normal path."""
+    import ctypes as C
+
+    import torch
+
+    from oscillink_b200 import _cabi
+
+    c = cases.build("perf_400")
+    lib = _cabi.load()
+    dev = torch.device("cuda")
+    Y = torch.from_numpy(c["Y"]).to(dev)
+    N, D = Y.shape
+    k, kc = 6, 10
+    Yn = torch.empty_like(Y)
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.osc_normalize_rows(Y.data_ptr(), N, D, Yn.data_ptr(), None, None, st))
+    ci = torch.empty((N, kc), dtype=torch.int32, device=dev)
+    cs = torch.empty((N, kc), dtype=torch.float32, device=dev)
+    _cabi.check(lib.osc_knn_candidates(Yn.data_ptr(), Yn.data_ptr(), None, None, None, None, 1, N, 0, N, D, kc,
+                                       _cabi.KNN_SIMT, ci.data_ptr(), cs.data_ptr(), None, 0, st))
+    need = C.c_size_t(0)
+    _cabi.check(lib.osc_knn_rescore_workspace(1, N, C.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    outs = []
+    for eps in (_cabi.KNN_EPS, 10.0):
+        ti = torch.empty((N, k), dtype=torch.int32, device=dev)
+        ts = torch.empty((N, k), dtype=torch.float32, device=dev)
+        gp = torch.empty(N, dtype=torch.float32, device=dev)
+        nf = torch.zeros(1, dtype=torch.int32, device=dev)
+        _cabi.check(lib.osc_knn_rescore_checked(Yn.data_ptr(), Yn.data_ptr(), 1, N, 0, N, D, ci.data_ptr(),
+                                                cs.data_ptr(), kc, k, eps, ti.data_ptr(), ts.data_ptr(),
+                                                gp.data_ptr(), nf.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        outs.append((ti.cpu().numpy(), ts.cpu().numpy(), gp.cpu().numpy(), int(nf.item())))
+    assert outs[0][3] == 0 and outs[1][3] == N
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
