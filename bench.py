@@ -381,7 +381,7 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    lat = ShardedLattice(Y_local, N, kneighbors=k, mode=args.partition)
+    lat = ShardedLattice(Y_local, N, kneighbors=k, mode="rows" if args.partition == "both" else args.partition)
     e1.record()
     barrier()
     build_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -393,93 +393,109 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
     lat.set_query(psi)
     if args.chain_len >= 2:
         lat.add_chain(list(range(args.chain_len)), lamP=0.2)
-    Y0 = lat._Y
+    def measure_mode(part):
+        Y0 = lat._Y
 
-    def one_settle():
-        lat._U = Y0.clone()
+        def one_settle():
+            lat._U = Y0.clone()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lat.set_query(psi_host.numpy())          # host psi -> device (the request's only host input)
+            st = lat.settle(max_iters=12, tol=1e-3)  # returns host {iters,res}: D2H inside
+            b.record()
+            barrier()
+            return a.elapsed_time(b), st
+
+        for _ in range(max(args.warmup, 1)):
+            one_settle()
+        with ClockSampler(local) as clk:
+            tot, st = 0.0, None
+            for _ in range(args.steps):
+                ms, st = one_settle()
+                tot += ms
+        clocks = clk.summary()
+        ms_settle = max_over_ranks(tot / args.steps)
+
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        lat.set_query(psi_host.numpy())          # host psi -> device (the request's only host input)
-        st = lat.settle(max_iters=12, tol=1e-3)  # returns host {iters,res}: D2H inside
-        b.record()
+        e0.record()
+        rec = lat.receipt()
+        e1.record()
         barrier()
-        return a.elapsed_time(b), st
+        receipt_ms = max_over_ranks(e0.elapsed_time(e1))
 
-    for _ in range(max(args.warmup, 1)):
-        one_settle()
-    with ClockSampler(local) as clk:
-        tot, st = 0.0, None
-        for _ in range(args.steps):
-            ms, st = one_settle()
-            tot += ms
-    clocks = clk.summary()
-    ms_settle = max_over_ranks(tot / args.steps)
+        # ---- per-kernel timings on the live state (one rank-local launch each, CUDA events)
+        Dl = D if part == "rows" else lat.Dl
+        n_loc = n_local if part == "rows" else N
+        lat._Ustar = None
+        X = lat._U  # clobbered below: the timed settles and the receipt are done
+        torch.cuda.empty_cache()
+        kf = _NativeKernels(lat, _cabi.MODE_SETTLE, 1.0, True, X, torch.zeros_like(X))
+        ones = torch.ones(Dl, dtype=torch.float32, device=dev)
 
-    barrier()
-    e0.record()
-    rec = lat.receipt()
-    e1.record()
-    barrier()
-    receipt_ms = max_over_ranks(e0.elapsed_time(e1))
-
-    # ---- per-kernel timings on the live state (one rank-local launch each, CUDA events)
-    Dl = D if args.partition == "rows" else lat.Dl
-    n_loc = n_local if args.partition == "rows" else N
-    lat._Ustar = None
-    X = lat._U  # clobbered below: the timed settles and the receipt are done
-    torch.cuda.empty_cache()
-    kf = _NativeKernels(lat, _cabi.MODE_SETTLE, 1.0, True, X, torch.zeros_like(X))
-    ones = torch.ones(Dl, dtype=torch.float32, device=dev)
-
-    def t_of(fn, reps=3):
-        fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
+        def t_of(fn, reps=3):
             fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
 
-    full = (lambda v: gather_rows(v, N, lat.group).contiguous()) if args.partition == "rows" else (lambda v: v)
-    x_all = full(X)
-    kf.residual0(x_all)
-    p_all = full(kf.P)
-    nnz = float(lat.nnz.item())
-    nnz_loc = nnz * n_loc / max(N, 1) if args.partition == "rows" else nnz
-    V = n_loc * Dl * 4.0
-    kms = {
-        "pcg_spmm": t_of(lambda: kf.spmm(p_all)),
-        "pcg_update": t_of(lambda: kf.update(ones, ones)),
-        "pcg_pupdate": t_of(lambda: kf.pupdate(ones, ones)),
-    }
-    if world > 1 and args.partition == "rows":
-        kms["halo_allgather_p"] = t_of(lambda: full(kf.P))
-    alg = {  # algorithmic bytes per launch
-        "pcg_spmm": (nnz_loc / max(n_loc, 1) + 2.0) * V + 8.0 * nnz_loc,
-        "pcg_update": 6.0 * V,
-        "pcg_pupdate": 3.0 * V,
-    }
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-        peak_src = "measured"
-    except Exception:
-        peaks = {"hbm_gbs": 6650.0}
-        peak_src = "fallback"
-    peak = float(peaks["hbm_gbs"])
-    gbs = {n: alg[n] / (kms[n] / 1000.0) / 1e9 for n in alg}
-    iters = int(st["iters"])
-    iter_bytes = alg["pcg_spmm"] + alg["pcg_update"] + alg["pcg_pupdate"]
-    solve_bytes = (iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"] + (iters - 1) * alg["pcg_pupdate"] + 4.0 * V
-    roof = {"kernel": "pcg_spmm_kernel", "bound": "hbm", "achieved": gbs["pcg_spmm"], "peak": peak,
-            "unit": "GB/s", "frac": gbs["pcg_spmm"] / peak, "traffic": None, "peak_source": peak_src,
-            "kernel_ms": kms, "kernel_gbs": gbs,
-            "whole_settle": {"algorithmic_bytes": solve_bytes, "achieved_gbs": solve_bytes / (ms_settle / 1e3) / 1e9,
-                             "frac": solve_bytes / (ms_settle / 1e3) / 1e9 / peak},
-            "bytes_per_iteration": iter_bytes}
+        full = (lambda v: gather_rows(v, N, lat.group).contiguous()) if part == "rows" else (lambda v: v)
+        x_all = full(X)
+        kf.residual0(x_all)
+        p_all = full(kf.P)
+        nnz = float(lat.nnz.item())
+        nnz_loc = nnz * n_loc / max(N, 1) if part == "rows" else nnz
+        V = n_loc * Dl * 4.0
+        kms = {
+            "pcg_spmm": t_of(lambda: kf.spmm(p_all)),
+            "pcg_update": t_of(lambda: kf.update(ones, ones)),
+            "pcg_pupdate": t_of(lambda: kf.pupdate(ones, ones)),
+        }
+        if world > 1 and part == "rows":
+            kms["halo_allgather_p"] = t_of(lambda: full(kf.P))
+        alg = {  # algorithmic bytes per launch
+            "pcg_spmm": (nnz_loc / max(n_loc, 1) + 2.0) * V + 8.0 * nnz_loc,
+            "pcg_update": 6.0 * V,
+            "pcg_pupdate": 3.0 * V,
+        }
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            peak_src = "measured"
+        except Exception:
+            peaks = {"hbm_gbs": 6650.0}
+            peak_src = "fallback"
+        peak = float(peaks["hbm_gbs"])
+        gbs = {n: alg[n] / (kms[n] / 1000.0) / 1e9 for n in alg}
+        iters = int(st["iters"])
+        iter_bytes = alg["pcg_spmm"] + alg["pcg_update"] + alg["pcg_pupdate"]
+        solve_bytes = (iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"] + (iters - 1) * alg["pcg_pupdate"] + 4.0 * V
+        roof = {"kernel": "pcg_spmm_kernel", "bound": "hbm", "achieved": gbs["pcg_spmm"], "peak": peak,
+                "unit": "GB/s", "frac": gbs["pcg_spmm"] / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kms, "kernel_gbs": gbs,
+                "whole_settle": {"algorithmic_bytes": solve_bytes, "achieved_gbs": solve_bytes / (ms_settle / 1e3) / 1e9,
+                                 "frac": solve_bytes / (ms_settle / 1e3) / 1e9 / peak},
+                "bytes_per_iteration": iter_bytes}
+        return dict(ms_settle=ms_settle, st=st, rec=rec, receipt_ms=receipt_ms, roof=roof, clocks=clocks, V=V,
+                    iters=iters, nnz=nnz)
+
+    first = "rows" if args.partition == "both" else args.partition
+    m = measure_mode(first)
+    ms_settle, st, rec, receipt_ms, roof, clocks, V, iters, nnz = (m[k] for k in (
+        "ms_settle", "st", "rec", "receipt_ms", "roof", "clocks", "V", "iters", "nnz"))
+    other = None
+    if args.partition == "both":
+        lat.repartition("columns")   # same graph, state transposed by one all-to-all
+        mc = measure_mode("columns")
+        other = {"parallelism": f"columns x{world}", "value": mc["ms_settle"], "unit": "ms",
+                 "roofline": mc["roof"], "receipt_light_ms": mc["receipt_ms"],
+                 "check": {"iters": int(mc["st"]["iters"]), "res": float(mc["st"]["res"]),
+                           "deltaH": mc["rec"]["deltaH_total"]}}
     line = None
     if rank == 0:
         line = {
@@ -489,7 +505,7 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
             "data": "synthetic",
             "config": {"workload": f"one lattice N={N} D={D} k={k} chain_len={args.chain_len}: "
                                    "step = settle(12,1e-3) from U=Y on the built mutual-kNN graph",
-                       "parallelism": f"{args.partition} x{world}",
+                       "parallelism": f"{first} x{world}",
                        "l2": f"vectors ({V / 1e9:.2f} GB each per GPU) larger than L2"},
             "e2e": {"value": ms_settle, "unit": "ms", "h2d_bytes_per_step": int(D * 4),
                     "d2h_bytes_per_step": 8,
@@ -502,7 +518,9 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
                       "avg_degree": rec["meta"]["avg_degree"], "nnz": nnz,
                       "rows_recomputed_exhaustively": int(getattr(lat, "n_exhaustive", torch.zeros(1)).item())},
         }
-    del lat, kf, X
+    if line is not None and other is not None:
+        line["columns_partition"] = other
+    del lat
     torch.cuda.empty_cache()
     return line
 
@@ -540,7 +558,7 @@ def main():
     ap.add_argument("--D", type=int, default=768)
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--chain-len", type=int, default=0)
-    ap.add_argument("--partition", default="rows", choices=["rows", "columns"])
+    ap.add_argument("--partition", default="rows", choices=["rows", "columns", "both"])
     ap.add_argument("--no-large", action="store_true",
                     help="serving workload only: skip the one-big-lattice block of the JSON line")
     args = ap.parse_args()

@@ -329,6 +329,59 @@ class ShardedLattice:
         torch.cuda.current_stream().synchronize()
         self.timings["graph_build_ms"] = 1000.0 * (time.time() - t0)
 
+    def repartition(self, mode: str) -> None:
+        """Switch between the row-block and the column-slab partition WITHOUT rebuilding the graph
+        (one all-to-all transposes the state from the layout the build wants to the layout
+        the solve wants).  Y and U move; the cached U* is dropped."""
+        import torch
+        import torch.distributed as dist
+
+        if mode not in {"rows", "columns"}:
+            raise ValueError("mode must be 'rows' or 'columns'")
+        if mode == self.mode:
+            return
+        G, N, D = self.world, self.N, self.D
+        if mode == "columns" and D % (4 * G) != 0:
+            raise ValueError("mode='columns' needs D divisible by 4*world_size")
+        nccl = G > 1 and dist.get_backend(self.group) == "nccl" and N % G == 0
+
+        def to_columns(t):  # [n_local, D] -> [N, D/G]
+            Dl = D // G
+            if G == 1:
+                return t
+            if nccl:
+                send = t.view(self.n_local, G, Dl).permute(1, 0, 2).contiguous()  # [G][n_local][Dl]
+                recv = torch.empty((G, self.shard, Dl), dtype=t.dtype, device=t.device)
+                dist.all_to_all_single(recv, send, group=self.group)
+                return recv.view(N, Dl)
+            full = gather_rows(t, N, self.group)
+            return full[:, self.rank * Dl:(self.rank + 1) * Dl].contiguous()
+
+        def to_rows(t):  # [N, D/G] -> [n_local, D]
+            Dl = D // G
+            if G == 1:
+                return t
+            if nccl:
+                send = t.view(G, self.shard, Dl).contiguous()
+                recv = torch.empty((G, self.n_local, Dl), dtype=t.dtype, device=t.device)
+                dist.all_to_all_single(recv, send, group=self.group)
+                return recv.permute(1, 0, 2).contiguous().view(self.n_local, D)
+            src = t.contiguous()
+            if dist.get_backend(self.group) == "gloo":
+                src = src.cpu()
+            parts = [torch.empty_like(src) for _ in range(G)]
+            dist.all_gather(parts, src, group=self.group)
+            full = torch.cat(parts, dim=1).to(t.device)
+            return full[self.row0:self.row0 + self.n_local].contiguous()
+
+        move = to_columns if mode == "columns" else to_rows
+        self._Y, self._U = move(self._Y), move(self._U)
+        self.mode = mode
+        if mode == "columns":
+            self.Dl = D // G
+            self.c0 = self.rank * self.Dl
+        self._Ustar = None
+
     # ---- C-ABI structs
     def _graph_struct(self, local: bool):
         g = self._cabi.Graph

@@ -97,3 +97,60 @@ def test_sharded_matches_single_gpu(mode, case):
     if not cases.build(case)["second_settle"]:  # golden deltaH of gates_300 is after its 2nd settle
         assert rel(res["dH"][0], g["deltaH"]) < 1e-5
     assert res["U_err"] < 1e-6 and res["Us_err"] < 1e-6
+
+
+def _repartition_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cases
+        from oscillink_b200 import OscillinkLattice
+        from oscillink_b200.sharded_api import ShardedLattice, shard_bounds
+
+        c = cases.build("config2_1200")
+        Y = c["Y"]
+        N = Y.shape[0]
+        r0, nl, _ = shard_bounds(N, world, rank)
+        sl = ShardedLattice(Y[r0:r0 + nl], N, kneighbors=c["k"], mode="rows")
+        sl.set_query(c["psi"])
+        s1 = sl.settle()
+        U_rows = sl.U_full()
+        sl.repartition("columns")
+        same = bool(np.array_equal(U_rows, sl.U_full()))
+        s2 = sl.settle()           # second settle runs on column slabs, no graph rebuild
+        sl.repartition("rows")
+        U2 = sl.U_full()
+        out = None
+        if rank == 0:
+            ref = OscillinkLattice(Y, kneighbors=c["k"], deterministic_k=True)
+            ref.set_query(c["psi"])
+            r1 = ref.settle()
+            r2 = ref.settle()
+            out = {"same": same, "iters": (s1["iters"], r1["iters"], s2["iters"], r2["iters"]),
+                   "U2_err": float(np.linalg.norm(U2 - ref.U) / np.linalg.norm(ref.U))}
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_repartition_rows_columns_keeps_state_and_graph():
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_repartition_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    res = dict(q.get() for _ in range(world))[0]
+    assert res["same"]
+    assert res["iters"][0] == res["iters"][1] and res["iters"][2] == res["iters"][3]
+    assert res["U2_err"] < 1e-6
