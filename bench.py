@@ -346,7 +346,7 @@ def run_ours(args) -> None:
 
 
 # ----------------------------------------------------------------------------- large single lattice
-def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", world=1, rank=0, local=0):
+def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", world=1, rank=0, local=0, p2p=None):
     """BASELINE.json configs[3]/[4]: ONE big lattice (N up to 10M), kNN build + PCG settle, the rows
     (or column slabs) partitioned over the GPUs.  A step = one settle(12, 1e-3) from U = Y on the built
     lattice (the metric's `ms/settle`); build, U* + deltaH and the per-kernel rooflines ride along.
@@ -381,7 +381,8 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    lat = ShardedLattice(Y_local, N, kneighbors=k, mode="rows" if args.partition == "both" else args.partition)
+    lat = ShardedLattice(Y_local, N, kneighbors=k, mode="rows" if args.partition == "both" else args.partition,
+                         p2p=p2p)
     e1.record()
     barrier()
     build_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -428,7 +429,12 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
         Dl = D if part == "rows" else lat.Dl
         n_loc = n_local if part == "rows" else N
         lat._Ustar = None
-        X = lat._U  # clobbered below: the timed settles and the receipt are done
+        fused = part == "rows" and lat._want_p2p and lat._peers is not None
+        if fused:
+            X = lat._peers.X[:n_loc]
+            X.copy_(lat._U)
+        else:
+            X = lat._U  # clobbered below: the timed settles and the receipt are done
         torch.cuda.empty_cache()
         kf = _NativeKernels(lat, _cabi.MODE_SETTLE, 1.0, True, X, torch.zeros_like(X))
         ones = torch.ones(Dl, dtype=torch.float32, device=dev)
@@ -444,9 +450,14 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
 
-        full = (lambda v: gather_rows(v, N, lat.group).contiguous()) if part == "rows" else (lambda v: v)
+        gather = lambda v: gather_rows(v, N, lat.group).contiguous()  # noqa: E731
+        if fused:
+            full = lambda v: (kf.peer_sync(), None)[1]  # noqa: E731
+        else:
+            full = gather if part == "rows" else (lambda v: v)
         x_all = full(X)
         kf.residual0(x_all)
+        del x_all
         p_all = full(kf.P)
         nnz = float(lat.nnz.item())
         nnz_loc = nnz * n_loc / max(N, 1) if part == "rows" else nnz
@@ -457,7 +468,9 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
             "pcg_pupdate": t_of(lambda: kf.pupdate(ones, ones)),
         }
         if world > 1 and part == "rows":
-            kms["halo_allgather_p"] = t_of(lambda: full(kf.P))
+            # what the un-fused schedule pays in front of every SpMM (for reference when fused)
+            kms["halo_allgather_p"] = t_of(lambda: gather(kf.P))
+            kms["halo"] = "fused: peers' rows read over NVLink inside pcg_spmm" if fused else "NCCL all-gather"
         alg = {  # algorithmic bytes per launch
             "pcg_spmm": (nnz_loc / max(n_loc, 1) + 2.0) * V + 8.0 * nnz_loc,
             "pcg_update": 6.0 * V,
@@ -472,6 +485,11 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
             peak_src = "fallback"
         peak = float(peaks["hbm_gbs"])
         gbs = {n: alg[n] / (kms[n] / 1000.0) / 1e9 for n in alg}
+        if fused:  # the SpMM is now bounded by NVLink for the remote share of its gathers
+            roof_note = ("rows partition with the halo fused: (world-1)/world of the gathered rows arrive over "
+                         "NVLink (~775 GB/s per GPU measured for LDG.128 peer reads), not HBM")
+        else:
+            roof_note = None
         iters = int(st["iters"])
         iter_bytes = alg["pcg_spmm"] + alg["pcg_update"] + alg["pcg_pupdate"]
         solve_bytes = (iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"] + (iters - 1) * alg["pcg_pupdate"] + 4.0 * V
@@ -489,13 +507,21 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
     ms_settle, st, rec, receipt_ms, roof, clocks, V, iters, nnz = (m[k] for k in (
         "ms_settle", "st", "rec", "receipt_ms", "roof", "clocks", "V", "iters", "nnz"))
     other = None
+    halo_first = "fused P2P" if lat._want_p2p else "NCCL all-gather"
+    other_halo = None
     if args.partition == "both":
+        def brief(mm, par):
+            return {"parallelism": par, "value": mm["ms_settle"], "unit": "ms", "roofline": mm["roof"],
+                    "receipt_light_ms": mm["receipt_ms"],
+                    "check": {"iters": int(mm["st"]["iters"]), "res": float(mm["st"]["res"]),
+                              "deltaH": mm["rec"]["deltaH_total"]}}
+
+        if world > 1:  # the other halo strategy of the rows partition, same graph
+            lat.set_halo(not lat._want_p2p)
+            mh = measure_mode("rows")
+            other_halo = brief(mh, f"rows x{world} ({'fused P2P' if lat._want_p2p else 'NCCL all-gather'} halo)")
         lat.repartition("columns")   # same graph, state transposed by one all-to-all
-        mc = measure_mode("columns")
-        other = {"parallelism": f"columns x{world}", "value": mc["ms_settle"], "unit": "ms",
-                 "roofline": mc["roof"], "receipt_light_ms": mc["receipt_ms"],
-                 "check": {"iters": int(mc["st"]["iters"]), "res": float(mc["st"]["res"]),
-                           "deltaH": mc["rec"]["deltaH_total"]}}
+        other = brief(measure_mode("columns"), f"columns x{world}")
     line = None
     if rank == 0:
         line = {
@@ -505,7 +531,8 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
             "data": "synthetic",
             "config": {"workload": f"one lattice N={N} D={D} k={k} chain_len={args.chain_len}: "
                                    "step = settle(12,1e-3) from U=Y on the built mutual-kNN graph",
-                       "parallelism": f"{first} x{world}",
+                       "parallelism": f"{first} x{world}" + (f" ({halo_first} halo)"
+                                                              if (first == "rows" and world > 1) else ""),
                        "l2": f"vectors ({V / 1e9:.2f} GB each per GPU) larger than L2"},
             "e2e": {"value": ms_settle, "unit": "ms", "h2d_bytes_per_step": int(D * 4),
                     "d2h_bytes_per_step": 8,
@@ -520,6 +547,9 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="rows", worl
         }
     if line is not None and other is not None:
         line["columns_partition"] = other
+    if line is not None and other_halo is not None:
+        line["rows_other_halo"] = other_halo
+    lat.close()
     del lat
     torch.cuda.empty_cache()
     return line
@@ -536,7 +566,8 @@ def run_large(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     line = measure_large(args.N, args.D, args.k, steps=args.steps, warmup=args.warmup, chain_len=args.chain_len,
-                         partition=args.partition, world=world, rank=rank, local=local)
+                         partition=args.partition, world=world, rank=rank, local=local,
+                         p2p=False if args.no_p2p else None)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -559,6 +590,8 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--chain-len", type=int, default=0)
     ap.add_argument("--partition", default="rows", choices=["rows", "columns", "both"])
+    ap.add_argument("--no-p2p", action="store_true",
+                    help="large workload, rows partition: NCCL all-gather halo instead of the fused P2P halo")
     ap.add_argument("--no-large", action="store_true",
                     help="serving workload only: skip the one-big-lattice block of the JSON line")
     args = ap.parse_args()

@@ -189,6 +189,30 @@ int osc_pcg_spmm_dot(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc
                      const osc_params_t* prm, int32_t mode, float dt, const float* gates_loc,
                      const float* P_all, float* AP_loc, double* part_pap, void* stream);
 
+/* Row-sharded SpMM with the halo exchange FUSED into the kernel (north_star "U halo rows are
+ * exchanged per SpMM"): d_peer_* is a device array of `world` pointers, entry r = base of rank r's
+ * block of `shard` rows ([shard][D] fp32) in rank r's HBM, mapped into this process with CUDA IPC.
+ * Neighbour rows owned by another rank are read by plain loads over NVLink while the tile is being
+ * computed -- no all-gather in front of the SpMM, no N x D staging buffer.  The caller orders the
+ * phases across ranks (every rank's writes to its block complete before any peer's SpMM starts).
+ * osc_enable_peer_access(peer) must have been called once per peer device in this process. */
+int osc_enable_peer_access(int32_t peer_device);
+/* Peer-mapped row blocks: osc_peer_alloc = cudaMalloc (zero-filled) + cudaIpcGetMemHandle (64-byte
+ * handle, to be sent to the peer processes); osc_peer_open = cudaIpcOpenMemHandle with lazy peer
+ * access from the CURRENT device of the calling process; osc_peer_close / osc_peer_free undo them. */
+int osc_peer_alloc(size_t bytes, void** d_ptr, unsigned char* handle64);
+int osc_peer_open(const unsigned char* handle64, void** d_ptr);
+int osc_peer_close(void* d_ptr);
+int osc_peer_free(void* d_ptr);
+int osc_pcg_residual0_p2p(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                          const osc_params_t* prm, int32_t mode, float dt, int32_t jacobi,
+                          const float* gates_loc, const float* const* d_peer_X, int32_t world, int64_t shard,
+                          float* RBv_loc, float* P_loc, double* part_rz, void* stream);
+int osc_pcg_spmm_dot_p2p(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                         const osc_params_t* prm, int32_t mode, float dt, const float* gates_loc,
+                         const float* const* d_peer_P, int32_t world, int64_t shard, float* AP_loc,
+                         double* part_pap, void* stream);
+
 /* column reduction of the row-block partials: out[D] (fp32) = sum_blocks part[b][D];
  * if h_or_d_max != NULL also writes max_c sqrt(out[c]) to *d_max (device float). */
 int osc_pcg_reduce(const double* part, int32_t n_blocks, int32_t D, float* out, float* d_max,

@@ -80,6 +80,16 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osc_pcg_spmm_dot": (C.c_int, [P(PcgDims), P(Graph), P(Chain), P(Params), c_i32, c_f32, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osc_enable_peer_access": (C.c_int, [c_i32]),
+    "osc_peer_alloc": (C.c_int, [c_size_t, P(c_void_p), c_void_p]),
+    "osc_peer_open": (C.c_int, [c_void_p, P(c_void_p)]),
+    "osc_peer_close": (C.c_int, [c_void_p]),
+    "osc_peer_free": (C.c_int, [c_void_p]),
+    "osc_pcg_residual0_p2p": (C.c_int, [P(PcgDims), P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32,
+                                        c_void_p, c_void_p, c_i32, c_i64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    "osc_pcg_spmm_dot_p2p": (C.c_int, [P(PcgDims), P(Graph), P(Chain), P(Params), c_i32, c_f32, c_void_p,
+                                       c_void_p, c_i32, c_i64, c_void_p, c_void_p, c_void_p]),
     "osc_pcg_reduce": (C.c_int, [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
     "osc_pcg_update": (C.c_int, [P(PcgDims), P(Params), c_i32, c_f32, c_i32, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

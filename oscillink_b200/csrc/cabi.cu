@@ -53,6 +53,11 @@ int pcg_residual0(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*,
                   int, float, int, const float*, const float*, float*, float*, double*, cudaStream_t);
 int pcg_spmm_dot(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
                  int, float, const float*, const float*, float*, double*, cudaStream_t);
+int pcg_residual0_p2p(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
+                      int, float, int, const float*, const float* const*, int64_t, float*, float*, double*,
+                      cudaStream_t);
+int pcg_spmm_dot_p2p(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
+                     int, float, const float*, const float* const*, int64_t, float*, double*, cudaStream_t);
 int pcg_reduce(const double*, int, int, float*, float*, double*, cudaStream_t);
 int pcg_update(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, const float*, const float*,
                const float*, const float*, const float*, float*, float*, double*, double*,
@@ -303,6 +308,82 @@ int osc_pcg_spmm_dot(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc
   OSC_REQUIRE(dims && g && prm && P_all && AP_loc && part_pap, "pcg_spmm_dot: NULL argument");
   return pcg_spmm_dot(dims, g, chain, prm, mode, dt, gates_loc, P_all, AP_loc, part_pap,
                       (cudaStream_t)stream);
+}
+
+int osc_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  OSC_CUDA(cudaGetDevice(&dev));
+  if (peer_device == dev) return OSC_OK;
+  int can = 0;
+  OSC_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) return fail(OSC_ERR_UNSUPPORTED, "enable_peer_access: no P2P path between the two devices");
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();  // clear the sticky-free error state
+    return OSC_OK;
+  }
+  OSC_CUDA(e);
+  return OSC_OK;
+}
+
+// Peer-mapped buffers: a plain cudaMalloc allocation (so the IPC handle covers exactly this buffer,
+// offset 0) exported with cudaIpcGetMemHandle; a peer process maps it from ITS device with
+// cudaIpcOpenMemHandle(..., cudaIpcMemLazyEnablePeerAccess), which also enables NVLink peer access.
+int osc_peer_alloc(size_t bytes, void** d_ptr, unsigned char* handle64) {
+  OSC_REQUIRE(d_ptr != nullptr && handle64 != nullptr && bytes > 0, "peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  OSC_CUDA(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e, "peer_alloc");
+  }
+  memcpy(handle64, &h, 64);
+  *d_ptr = p;
+  return OSC_OK;
+}
+
+int osc_peer_open(const unsigned char* handle64, void** d_ptr) {
+  OSC_REQUIRE(d_ptr != nullptr && handle64 != nullptr, "peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  OSC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_ptr = p;
+  return OSC_OK;
+}
+
+int osc_peer_close(void* d_ptr) {
+  if (d_ptr != nullptr) OSC_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return OSC_OK;
+}
+
+int osc_peer_free(void* d_ptr) {
+  if (d_ptr != nullptr) OSC_CUDA(cudaFree(d_ptr));
+  return OSC_OK;
+}
+
+int osc_pcg_residual0_p2p(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                          const osc_params_t* prm, int32_t mode, float dt, int32_t jacobi,
+                          const float* gates_loc, const float* const* d_peer_X, int32_t world, int64_t shard,
+                          float* RBv_loc, float* P_loc, double* part_rz, void* stream) {
+  OSC_REQUIRE(dims && g && prm && d_peer_X && RBv_loc && P_loc && part_rz, "pcg_residual0_p2p: NULL argument");
+  OSC_REQUIRE(world >= 1 && shard >= 1 && (int64_t)world * shard >= dims->N, "pcg_residual0_p2p: bad partition");
+  return pcg_residual0_p2p(dims, g, chain, prm, mode, dt, jacobi, gates_loc, d_peer_X, shard, RBv_loc, P_loc,
+                           part_rz, (cudaStream_t)stream);
+}
+
+int osc_pcg_spmm_dot_p2p(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
+                         const osc_params_t* prm, int32_t mode, float dt, const float* gates_loc,
+                         const float* const* d_peer_P, int32_t world, int64_t shard, float* AP_loc,
+                         double* part_pap, void* stream) {
+  OSC_REQUIRE(dims && g && prm && d_peer_P && AP_loc && part_pap, "pcg_spmm_dot_p2p: NULL argument");
+  OSC_REQUIRE(world >= 1 && shard >= 1 && (int64_t)world * shard >= dims->N, "pcg_spmm_dot_p2p: bad partition");
+  return pcg_spmm_dot_p2p(dims, g, chain, prm, mode, dt, gates_loc, d_peer_P, shard, AP_loc, part_pap,
+                          (cudaStream_t)stream);
 }
 
 int osc_pcg_reduce(const double* part, int32_t n_blocks, int32_t D, float* out, float* d_max,

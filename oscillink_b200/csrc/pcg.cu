@@ -138,6 +138,21 @@ struct ChainView {
   const int32_t* slot;  // nullptr => no chain
 };
 
+// Where the gathered vector lives.  One GPU / all-gathered halo: `all` holds all N rows.  Row-sharded
+// P2P halo (osc_pcg_*_p2p): rank g's block of `shard` rows sits in peers[g], a buffer in GPU g's HBM
+// mapped into this process (CUDA IPC); remote rows are fetched by plain loads over NVLink inside the
+// SpMM, tile by tile, instead of an all-gather in front of it.
+struct VecView {
+  const float* all;           // [N][D] or nullptr
+  const float* const* peers;  // [world] device table of block base pointers, or nullptr
+  int64_t shard;
+};
+__device__ __forceinline__ const float* row_ptr(const VecView& v, int64_t j, int D) {
+  if (v.peers == nullptr) return v.all + j * D;
+  const int64_t g = j / v.shard;
+  return v.peers[g] + (j - g * v.shard) * D;
+}
+
 // RES0 = false: AP = Aop(V); part = sum_i V_i * AP_i
 // RES0 = true : R  = Bv - Aop(V) (in place over RBv); P = precond(R); part = sum_i R_i * Z_i
 //
@@ -151,13 +166,15 @@ constexpr int SPMM_RCH = 32;
 template <int VEC, bool RES0>
 __global__ void __launch_bounds__(256)
 pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
-                const float* __restrict__ Vall, float* __restrict__ out, float* __restrict__ Pout,
+                VecView vv, float* __restrict__ out, float* __restrict__ Pout,
                 double* __restrict__ part) {
   extern __shared__ double sh[];
   const int CG = dm.D / VEC;
   const int nthr = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  int32_t* s_nb = reinterpret_cast<int32_t*>(sh + (size_t)nthr * VEC);
+  // staged per chunk: the ADDRESS of every neighbour row (resolved once per chunk, not per column
+  // thread), its weight, the row degrees
+  const float** s_nb = reinterpret_cast<const float**>(sh + (size_t)nthr * VEC);
   float* s_w = reinterpret_cast<float*>(s_nb + SPMM_RCH * g.k);
   int32_t* s_deg = reinterpret_cast<int32_t*>(s_w + SPMM_RCH * g.k);
   const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
@@ -174,7 +191,8 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
     const int rows = (int)min((int64_t)SPMM_RCH, r_end - c0);
     __syncthreads();  // the previous chunk's readers are done
     for (int e = tid; e < rows * g.k; e += nthr) {
-      s_nb[e] = g.nbr[c0 * g.k + e];
+      const int32_t j = g.nbr[c0 * g.k + e];
+      s_nb[e] = j >= 0 ? row_ptr(vv, j, dm.D) : nullptr;
       s_w[e] = g.W[c0 * g.k + e];
     }
     for (int e = tid; e < rows; e += nthr) s_deg[e] = g.deg[c0 + e];
@@ -184,17 +202,17 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
       const int64_t i = c0 + lr;
       const int64_t gi = dm.row0 + i;
       float own[VEC], s[VEC];
-      ldv<VEC>(Vall + gi * dm.D + co, own);
+      ldv<VEC>(row_ptr(vv, gi, dm.D) + co, own);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s[v] = 0.f;
       const int n = s_deg[lr];
-      const int32_t* nb = s_nb + lr * g.k;
+      const float* const* nb = s_nb + lr * g.k;
       const float* wt = s_w + lr * g.k;
       int t = 0;
       for (; t + 8 <= n; t += 8) {
         float x[8][VEC];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) ldv<VEC>(Vall + (int64_t)nb[t + u] * dm.D + co, x[u]);
+        for (int u = 0; u < 8; ++u) ldv<VEC>(nb[t + u] + co, x[u]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const float w = wt[t + u];
@@ -205,7 +223,7 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
       if (t + 4 <= n) {
         float x[4][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) ldv<VEC>(Vall + (int64_t)nb[t + u] * dm.D + co, x[u]);
+        for (int u = 0; u < 4; ++u) ldv<VEC>(nb[t + u] + co, x[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float w = wt[t + u];
@@ -216,7 +234,7 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
       }
       for (; t < n; ++t) {
         float x[VEC];
-        ldv<VEC>(Vall + (int64_t)nb[t] * dm.D + co, x);
+        ldv<VEC>(nb[t] + co, x);
         const float w = wt[t];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[v], s[v]);
@@ -234,7 +252,7 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
           for (int v = 0; v < VEC; ++v) sp[v] = 0.f;
           for (int e = ch.rowptr[sl]; e < ch.rowptr[sl + 1]; ++e) {
             float x[VEC];
-            ldv<VEC>(Vall + (int64_t)ch.col[e] * dm.D + co, x);
+            ldv<VEC>(row_ptr(vv, ch.col[e], dm.D) + co, x);
             const float w = ch.Wp[e];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) sp[v] = fmaf(w, x[v], sp[v]);
@@ -477,25 +495,25 @@ int pcg_setup(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float 
 
 static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
                        const osc_chain_t* chain, const osc_params_t* prm, int mode, float dt,
-                       int jacobi, const float* gates, const float* Vall, float* out, float* Pout,
+                       int jacobi, const float* gates, VecView vv, float* out, float* Pout,
                        double* part, cudaStream_t st) {
   if (d->n_local == 0) return OSC_OK;
   int vec;
   dim3 blk;
   block_shape(d->D, vec, blk);
-  if (!(aligned16(Vall) && aligned16(out) && (Pout == nullptr || aligned16(Pout)))) {
+  if (!((vv.all == nullptr || aligned16(vv.all)) && aligned16(out) && (Pout == nullptr || aligned16(Pout)))) {
     if (vec == 4) return fail(OSC_ERR_INVALID, "pcg: vectors must be 16-byte aligned when D % 4 == 0");
   }
   Coef c = make_coef(prm, mode, dt, jacobi);
   const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double) +
-                      (size_t)SPMM_RCH * (g->k * 8 + 4);
+                      (size_t)SPMM_RCH * (g->k * 12 + 4);
   const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
   if (res0) {
     OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, true><<<grid, blk, smem, st>>>(
-                              to_dims(d), c, gview(g), cview(chain), gates, Vall, out, Pout, part);)
+                              to_dims(d), c, gview(g), cview(chain), gates, vv, out, Pout, part);)
   } else {
     OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, false><<<grid, blk, smem, st>>>(
-                              to_dims(d), c, gview(g), cview(chain), gates, Vall, out, Pout, part);)
+                              to_dims(d), c, gview(g), cview(chain), gates, vv, out, Pout, part);)
   }
   OSC_LAUNCH_CHECK("pcg_spmm_kernel");
   return OSC_OK;
@@ -504,13 +522,30 @@ static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
 int pcg_residual0(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                   const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates,
                   const float* Xall, float* RBv, float* P, double* part_rz, cudaStream_t st) {
-  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, Xall, RBv, P, part_rz, st);
+  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, VecView{Xall, nullptr, 0}, RBv, P,
+                     part_rz, st);
+}
+
+int pcg_residual0_p2p(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
+                      const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates,
+                      const float* const* peers, int64_t shard, float* RBv, float* P, double* part_rz,
+                      cudaStream_t st) {
+  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, VecView{nullptr, peers, shard}, RBv, P,
+                     part_rz, st);
 }
 
 int pcg_spmm_dot(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                  const osc_params_t* prm, int mode, float dt, const float* gates, const float* Pall,
                  float* AP, double* part_pap, cudaStream_t st) {
-  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, Pall, AP, nullptr, part_pap, st);
+  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, VecView{Pall, nullptr, 0}, AP, nullptr,
+                     part_pap, st);
+}
+
+int pcg_spmm_dot_p2p(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
+                     const osc_params_t* prm, int mode, float dt, const float* gates,
+                     const float* const* peers, int64_t shard, float* AP, double* part_pap, cudaStream_t st) {
+  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, VecView{nullptr, peers, shard}, AP, nullptr,
+                     part_pap, st);
 }
 
 int pcg_reduce(const double* part, int n_blocks, int D, float* out, float* d_max, double* out64,

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, mode, case, q):
+def _worker(rank, world, port, mode, case, q, p2p=None):
     import torch
     import torch.distributed as dist
 
@@ -36,7 +36,7 @@ def _worker(rank, world, port, mode, case, q):
         N = Y.shape[0]
         r0, nl, _ = shard_bounds(N, world, rank)
         sl = ShardedLattice(Y[r0:r0 + nl], N, kneighbors=c["k"], row_cap_val=c["cap"], lamG=c["lam"][0],
-                            lamC=c["lam"][1], lamQ=c["lam"][2], mode=mode)
+                            lamC=c["lam"][1], lamQ=c["lam"][2], mode=mode, p2p=p2p)
         sl.set_query(c["psi"], c["gates"])
         if c["chain"] is not None:
             sl.add_chain(c["chain"], lamP=c["lamP"], weights=c["weights"])
@@ -63,15 +63,20 @@ def _worker(rank, world, port, mode, case, q):
                 "U_err": float(np.linalg.norm(U - ref.U) / np.linalg.norm(ref.U)),
                 "Us_err": float(np.linalg.norm(Us - ref.solve_Ustar()) / np.linalg.norm(ref.solve_Ustar())),
             }
+        if out is not None:
+            out["p2p_used"] = sl._peers is not None
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,case", [("rows", "config2_1200"), ("columns", "config2_1200"),
-                                       ("rows", "perf_400"), ("columns", "perf_400"),
-                                       ("rows", "gates_300")])
-def test_sharded_matches_single_gpu(mode, case):
+@pytest.mark.parametrize("mode,case,p2p", [("rows", "config2_1200", None), ("columns", "config2_1200", None),
+                                           ("rows", "perf_400", None), ("columns", "perf_400", None),
+                                           ("rows", "gates_300", None),
+                                           # fused halo: peers' blocks read in place through CUDA IPC
+                                           ("rows", "config2_1200", True), ("rows", "perf_400", True),
+                                           ("rows", "gates_300", True)])
+def test_sharded_matches_single_gpu(mode, case, p2p):
     import torch.multiprocessing as mp
 
     from tests.helpers import load_golden, rel
@@ -79,7 +84,7 @@ def test_sharded_matches_single_gpu(mode, case):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, case, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -87,6 +92,7 @@ def test_sharded_matches_single_gpu(mode, case):
         assert p.exitcode == 0
     res = dict(q.get() for _ in range(world))[0]
     g, _ = load_golden(case)
+    assert res["p2p_used"] == bool(p2p)
     assert res["nbr_equal"]
     assert res["iters"][0] == res["iters"][1]
     assert rel(res["res"][0], res["res"][1]) < 1e-3

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--mode", default="rows")
     ap.add_argument("--chain", type=int, default=8)
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--p2p", type=int, default=-1, help="-1 auto (on under NCCL), 0 all-gather halo, 1 fused P2P halo")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -64,13 +65,15 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         return out, float(dt.item()) * 1e3
 
-    sl, t_build = timed(lambda: ShardedLattice(Yl, a.N, kneighbors=a.k, mode=a.mode))
+    sl, t_build = timed(lambda: ShardedLattice(Yl, a.N, kneighbors=a.k, mode=a.mode,
+                                                    p2p=None if a.p2p < 0 else bool(a.p2p)))
     sl.set_query(psi)
     if a.chain >= 2:
         sl.add_chain(list(range(a.chain)), lamP=0.2)
     st, t_settle = timed(lambda: sl.settle(max_iters=12, tol=1e-3))
     rec, t_rec = timed(sl.receipt)
-    res = {"N": a.N, "D": a.D, "k": a.k, "mode": a.mode, "world": world, "build_ms": t_build,
+    res = {"N": a.N, "D": a.D, "k": a.k, "mode": a.mode, "world": world, "p2p_halo": sl._peers is not None,
+           "build_ms": t_build,
            "settle_ms": t_settle, "receipt_ms": t_rec, "settle": {k: st[k] for k in ("iters", "res")},
            "deltaH": rec["deltaH_total"], "ustar_iters": rec["meta"]["ustar_iters"],
            "avg_degree": rec["meta"]["avg_degree"]}
@@ -99,6 +102,7 @@ def main():
             }
     if rank == 0:
         print(json.dumps(res))
+    sl.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
