@@ -275,6 +275,31 @@ class OscillinkLattice:
             dense[u, v] -= w
         return dense
 
+    def _load_ell_adjacency(self, nbr: np.ndarray, a: np.ndarray) -> None:
+        """from_state with the sparse graph format: adopt ELL rows (column ids ascending, -1 padded)
+        and recompute sqrt_deg / normalised weights as graph.py:87-90 does (row sums in fp32)."""
+        if nbr.ndim != 2 or nbr.shape != a.shape or nbr.shape[0] != self.N:
+            raise ValueError("A_ell shape mismatch")
+        if nbr.shape[1] == 0:
+            nbr = np.full((self.N, 1), -1, dtype=np.int32)
+            a = np.zeros((self.N, 1), dtype=_F32)
+        if np.any(nbr >= self.N):
+            raise ValueError("A_ell column index out of bounds")
+        a = np.where(nbr < 0, _F32(0), a).astype(_F32)
+        d = a.sum(axis=1, dtype=_F32)
+        sd = np.sqrt(np.maximum(d, _F32(1e-12))).astype(_F32)
+        inv = (_F32(1.0) / sd).astype(_F32)
+        safe = np.where(nbr < 0, 0, nbr)
+        w = ((a * inv[:, None]).astype(_F32) * inv[safe]).astype(_F32)
+        w[nbr < 0] = 0
+        dev = self._dev
+        self._nbr = torch.from_numpy(np.ascontiguousarray(nbr, dtype=np.int32)).to(dev)
+        self._A = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self._W = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
+        self._deg = torch.from_numpy((nbr >= 0).sum(axis=1).astype(np.int32)).to(dev)
+        self._sd = torch.from_numpy(sd).to(dev)
+        self._invalidate_graph_views()
+
     def _load_dense_adjacency(self, dense: np.ndarray) -> None:
         """from_state support (lattice.py:709-713): adopt a user-supplied dense adjacency and
         recompute sqrt_deg / normalised weights the way graph.py:87-90 does."""
@@ -848,7 +873,14 @@ class OscillinkLattice:
                                     "neighbor_seed": self._neighbor_seed})
 
     # ------------------------------------------------------------------ export / import
-    def export_state(self, include_graph: bool = True, include_chain: bool = True) -> dict[str, Any]:
+    def export_state(self, include_graph: bool = True, include_chain: bool = True, *,
+                     graph_format: str = "dense") -> dict[str, Any]:
+        """lattice.py:582-624.  graph_format="dense" (default) writes the reference's N x N `A`;
+        graph_format="ell" writes the adjacency the device holds -- `A_ell = {"nbr": [N][k] column ids
+        (-1 padded, ascending), "val": [N][k] weights}` -- O(N k) instead of O(N^2); `from_state`
+        accepts either."""
+        if graph_format not in {"dense", "ell"}:
+            raise ValueError("graph_format must be 'dense' or 'ell'")
         h = hashlib.sha256()
         h.update(self.Y.tobytes())
         h.update(self._hpsi.tobytes())
@@ -867,8 +899,11 @@ class OscillinkLattice:
             "neighbor_seed": self._neighbor_seed,
             "provenance": h.hexdigest(),
         }
-        if include_graph:
+        if include_graph and graph_format == "dense":
             state["A"] = self.A.tolist()
+        elif include_graph:
+            nbr, a = self._ell_host()
+            state["A_ell"] = {"nbr": nbr.tolist(), "val": a.tolist()}
         if include_chain and self._chain is not None:
             state["chain_edges"] = sorted([int(u), int(v)] for (u, v) in self._chain["ap_host"] if u < v)
             if self._chain_nodes is not None:
@@ -876,19 +911,23 @@ class OscillinkLattice:
         return state
 
     def save_state(self, path: str, format: str = "json", include_graph: bool = True,
-                   include_chain: bool = True) -> None:
+                   include_chain: bool = True, *, graph_format: str = "dense") -> None:
         fmt = format.lower()
-        state = self.export_state(include_graph=include_graph, include_chain=include_chain)
+        state = self.export_state(include_graph=include_graph, include_chain=include_chain,
+                                  graph_format=graph_format)
         if fmt == "json":
             with open(path, "w", encoding="utf-8") as f:
                 json.dump(state, f, sort_keys=True)
         elif fmt == "npz":
             arrays: dict[str, np.ndarray] = {"Y": self.Y, "psi": self._hpsi, "B_diag": self._hB}
-            if include_graph:
+            if include_graph and graph_format == "dense":
                 arrays["A"] = self.A
+            elif include_graph:
+                arrays["A_ell_nbr"], arrays["A_ell_val"] = self._ell_host()
             if include_chain and self._chain_nodes is not None:
                 arrays["chain_nodes"] = np.array(self._chain_nodes, dtype=np.int32)
-            meta = {k: v for k, v in state.items() if k not in {"Y", "psi", "B_diag", "A", "chain_nodes"}}
+            meta = {k: v for k, v in state.items()
+                    if k not in {"Y", "psi", "B_diag", "A", "A_ell", "chain_nodes"}}
             np.savez_compressed(path, __meta__=np.array(json.dumps(meta, sort_keys=True)), **arrays)
         else:
             raise ValueError("format must be 'json' or 'npz'")
@@ -902,6 +941,8 @@ class OscillinkLattice:
             state["B_diag"] = data["B_diag"].astype(_F32)
             if "A" in data.files:
                 state["A"] = data["A"].astype(_F32)
+            if "A_ell_nbr" in data.files:
+                state["A_ell"] = {"nbr": data["A_ell_nbr"], "val": data["A_ell_val"]}
             if "chain_nodes" in data.files:
                 state["chain_nodes"] = data["chain_nodes"].astype(int).tolist()
         return cls.from_state(state)
@@ -921,6 +962,9 @@ class OscillinkLattice:
             A = np.array(state["A"], dtype=_F32)
             if A.shape == (lat.N, lat.N):
                 lat._load_dense_adjacency(A)
+        elif "A_ell" in state:
+            lat._load_ell_adjacency(np.asarray(state["A_ell"]["nbr"], dtype=np.int32),
+                                    np.asarray(state["A_ell"]["val"], dtype=_F32))
         lamP = params.get("lamP", 0.0)
         if lamP > 0:
             if "chain_nodes" in state:

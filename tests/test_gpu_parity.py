@@ -401,3 +401,42 @@ def test_exhaustive_rows_equal_candidate_rows(api):
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_sparse_state_format_roundtrip(api, tmp_path):
+    """Row f4: the O(N k) ELL state format restores the same lattice as the reference's dense format
+    (lattice.py:582-726): identical signature, identical graph, deltaH within the reference test's bound
+    (tests/test_export_import_and_cache.py:6-25 allows 1e-2; here 1e-6)."""
+    c = cases.build("perf_400")
+    lat = _make(api, c)
+    lat.settle()
+    lat.set_receipt_detail("light")
+    dh = lat.receipt()["deltaH_total"]
+    st_d = lat.export_state()
+    st_s = lat.export_state(graph_format="ell")
+    assert "A" in st_d and "A_ell" in st_s and "A" not in st_s
+    assert st_d["provenance"] == st_s["provenance"]
+    assert len(st_s["A_ell"]["nbr"]) == lat.N and len(st_s["A_ell"]["nbr"][0]) == lat._nbr.shape[1]
+    with pytest.raises(ValueError):
+        lat.export_state(graph_format="csr")
+    for fmt in ("json", "npz"):
+        path = str(tmp_path / f"state_ell.{fmt}")
+        lat.save_state(path, format=fmt, graph_format="ell")
+        if fmt == "npz":
+            back = api.OscillinkLattice.from_npz(path)
+        else:
+            import json
+
+            with open(path) as f:
+                back = api.OscillinkLattice.from_state(json.load(f))
+        assert back._signature() == lat._signature()
+        assert np.array_equal(back._nbr.cpu().numpy(), lat._nbr.cpu().numpy())
+        np.testing.assert_allclose(back._W.cpu().numpy(), lat._W.cpu().numpy(), rtol=6e-7, atol=0)
+        back.settle()
+        back.set_receipt_detail("light")
+        assert rel(back.receipt()["deltaH_total"], dh) < 1e-6
+    # the dense and the sparse import agree with each other
+    bd = api.OscillinkLattice.from_state(st_d)
+    bs = api.OscillinkLattice.from_state(st_s)
+    assert np.array_equal(bd._nbr.cpu().numpy(), bs._nbr.cpu().numpy())
+    np.testing.assert_allclose(bd._W.cpu().numpy(), bs._W.cpu().numpy(), rtol=6e-7, atol=0)
