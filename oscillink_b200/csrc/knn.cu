@@ -164,19 +164,48 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
   const float* yi = Yq + (b * n_rows + r) * D;
   const float* all = Yall + b * N * D;
   const int32_t* ci = cand_idx + (b * n_rows + r) * kc;
-  for (int c = 0; c < kc; ++c) {
-    const int j = ci[c];
-    float s = -INFINITY;
-    if (j >= 0) {
-      const float* yj = all + (int64_t)j * D;
-      double acc = 0.0;
-      for (int d = lane; d < D; d += 32) acc = fma((double)yi[d], (double)yj[d], acc);
-      acc = warp_sum(acc);
-      s = (float)acc;
+  // Four candidates at a time: their row fetches are independent, so a lane keeps up to 4 x D/128
+  // 16-byte loads in flight (the pass is bound by L2/HBM latency, not by the fp64 FMAs).  Lane l
+  // owns elements {4l..4l+3} + 128 t of every row, for (i,j) and (j,i) alike: S stays symmetric.
+  const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(yi) | reinterpret_cast<uintptr_t>(all)) % 16 == 0);
+  for (int c0 = 0; c0 < kc; c0 += 4) {
+    int jc[4];
+    const float* yj[4];
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      jc[u] = (c0 + u < kc) ? ci[c0 + u] : -1;
+      yj[u] = all + (int64_t)(jc[u] >= 0 ? jc[u] : 0) * D;
+      acc[u] = 0.0;
     }
-    if (lane == 0) {
-      sv[c] = s;
-      sj[c] = j;
+    if (v4) {
+      for (int d = lane * 4; d < D; d += 128) {
+        const float4 q = *reinterpret_cast<const float4*>(yi + d);
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(yj[u] + d);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u] = fma((double)q.x, (double)x[u].x, acc[u]);
+          acc[u] = fma((double)q.y, (double)x[u].y, acc[u]);
+          acc[u] = fma((double)q.z, (double)x[u].z, acc[u]);
+          acc[u] = fma((double)q.w, (double)x[u].w, acc[u]);
+        }
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const double q = (double)yi[d];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(q, (double)yj[u][d], acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double t = warp_sum(acc[u]);
+      if (lane == 0 && c0 + u < kc) {
+        sv[c0 + u] = jc[u] >= 0 ? (float)t : -INFINITY;
+        sj[c0 + u] = jc[u];
+      }
     }
   }
   __syncwarp();
@@ -243,12 +272,24 @@ knn_exact_rows_kernel(const float* __restrict__ Yq, const float* __restrict__ Ya
     const int64_t self = row0 + r;
     const float* yi = Yq + gid * D;
     const float* all = Yall + b * N * D;
+    const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(yi) | reinterpret_cast<uintptr_t>(all)) % 16 == 0);
     int cnt = 0;
     for (int64_t j = w; j < N; j += warps) {
       if (j == self) continue;
       const float* yj = all + j * D;
       double acc = 0.0;
-      for (int d = lane; d < D; d += 32) acc = fma((double)yi[d], (double)yj[d], acc);
+      if (v4) {  // same element ownership / order per lane as knn_rescore_kernel: bit-identical scores
+        for (int d = lane * 4; d < D; d += 128) {
+          const float4 q = *reinterpret_cast<const float4*>(yi + d);
+          const float4 x = *reinterpret_cast<const float4*>(yj + d);
+          acc = fma((double)q.x, (double)x.x, acc);
+          acc = fma((double)q.y, (double)x.y, acc);
+          acc = fma((double)q.z, (double)x.z, acc);
+          acc = fma((double)q.w, (double)x.w, acc);
+        }
+      } else {
+        for (int d = lane; d < D; d += 32) acc = fma((double)yi[d], (double)yj[d], acc);
+      }
       acc = warp_sum(acc);
       const float sc = (float)acc;
       if (lane == 0 && (cnt < L || better(sc, (int)j, lv[L - 1], li[L - 1]))) {
