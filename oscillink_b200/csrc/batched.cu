@@ -204,10 +204,12 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   float4* redA = red;               // init r.z, then p.Ap
   float4* redB = red + RED_F4;      // r.r
   float4* redC = red + 2 * RED_F4;  // r.z'
+  // Rows tid + T*m >= N are PAD rows: zero state, zero weights, neighbour offset 0.  They run through
+  // every phase unguarded (all their values stay 0 and add 0 to the reductions), which keeps the
+  // per-row work free of per-thread branches so the compiler interleaves the TPT rows' load chains.
   if (acc_in == nullptr) {
 #pragma unroll
-    for (int m = 0; m < TPT; ++m)
-      if (act[m]) p_s[tid + T * m] = st.X[m];
+    for (int m = 0; m < TPT; ++m) p_s[tid + T * m] = st.X[m];
   }
   __syncthreads();  // x0 visible; diag_s, im_s of this solve visible
   // ---- r0 = b - A x0 ; z0 ; rz
@@ -215,31 +217,27 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   float4 part = f4_zero();
 #pragma unroll
   for (int m = 0; m < TPT; ++m) {
-    z0[m] = f4_zero();
-    if (act[m]) {
-      const int row = tid + T * m;
-      const float imr = im_s ? im_s[row] : c.im_u;
-      float4 g;
-      if (acc_in != nullptr) {
-        g = acc_in[row];
-      } else {
-        g = gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq);
-        if (acc_out != nullptr) acc_out[row] = g;
-      }
-      const float4 a = combine_row(st.X[m], g, diag_s ? diag_s[row] : c.diag_u, c.offc);
-      float4 r = st.R[m];
-      r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
-      st.R[m] = r;
-      z0[m] = make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr);
-      part = f4_add(part, f4_mul(r, z0[m]));
+    const int row = tid + T * m;
+    const float imr = im_s ? im_s[row] : c.im_u;
+    float4 g;
+    if (acc_in != nullptr) {
+      g = act[m] ? acc_in[row] : f4_zero();
+    } else {
+      g = gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq);
+      if (acc_out != nullptr && act[m]) acc_out[row] = g;
     }
+    const float4 a = combine_row(st.X[m], g, diag_s ? diag_s[row] : c.diag_u, c.offc);
+    float4 r = st.R[m];
+    r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
+    st.R[m] = r;
+    z0[m] = make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr);
+    part = f4_add(part, f4_mul(r, z0[m]));
   }
   warp_reduce4(part, redA + warp, lane);
   __syncthreads();  // also: every gather of x0 has completed
   float rz = block_total_c(redA, nw, lane);  // component lane&3
 #pragma unroll
-  for (int m = 0; m < TPT; ++m)
-    if (act[m]) p_s[tid + T * m] = z0[m];
+  for (int m = 0; m < TPT; ++m) p_s[tid + T * m] = z0[m];
   __syncthreads();
 
   int it = 1;
@@ -249,13 +247,11 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     part = f4_zero();
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
-      if (act[m]) {
-        const int row = tid + T * m;
-        const float4 own = p_s[row];
-        st.AP[m] = combine_row(own, gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq),
-                               diag_s ? diag_s[row] : c.diag_u, c.offc);
-        part = f4_add(part, f4_mul(own, st.AP[m]));
-      }
+      const int row = tid + T * m;
+      const float4 own = p_s[row];
+      st.AP[m] = combine_row(own, gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq),
+                             diag_s ? diag_s[row] : c.diag_u, c.offc);
+      part = f4_add(part, f4_mul(own, st.AP[m]));
     }
     warp_reduce4(part, redA + warp, lane);
     __syncthreads();
@@ -266,24 +262,21 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     float4 zz[TPT];
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
-      zz[m] = f4_zero();
-      if (act[m]) {
-        const int row = tid + T * m;
-        const float4 p = p_s[row];
-        float4 x = st.X[m], r = st.R[m];
-        const float4 ap = st.AP[m];
-        x = make_float4(fmaf(p.x, alpha.x, x.x), fmaf(p.y, alpha.y, x.y), fmaf(p.z, alpha.z, x.z),
-                        fmaf(p.w, alpha.w, x.w));
-        r = make_float4(fmaf(-ap.x, alpha.x, r.x), fmaf(-ap.y, alpha.y, r.y), fmaf(-ap.z, alpha.z, r.z),
-                        fmaf(-ap.w, alpha.w, r.w));
-        st.X[m] = x;
-        st.R[m] = r;
-        const float im = im_s ? im_s[row] : c.im_u;
-        const float4 z = make_float4(r.x * im, r.y * im, r.z * im, r.w * im);
-        zz[m] = z;
-        prr = f4_add(prr, f4_mul(r, r));
-        prz = f4_add(prz, f4_mul(r, z));
-      }
+      const int row = tid + T * m;
+      const float4 p = p_s[row];
+      float4 x = st.X[m], r = st.R[m];
+      const float4 ap = st.AP[m];
+      x = make_float4(fmaf(p.x, alpha.x, x.x), fmaf(p.y, alpha.y, x.y), fmaf(p.z, alpha.z, x.z),
+                      fmaf(p.w, alpha.w, x.w));
+      r = make_float4(fmaf(-ap.x, alpha.x, r.x), fmaf(-ap.y, alpha.y, r.y), fmaf(-ap.z, alpha.z, r.z),
+                      fmaf(-ap.w, alpha.w, r.w));
+      st.X[m] = x;
+      st.R[m] = r;
+      const float im = im_s ? im_s[row] : c.im_u;
+      const float4 z = make_float4(r.x * im, r.y * im, r.z * im, r.w * im);
+      zz[m] = z;
+      prr = f4_add(prr, f4_mul(r, r));
+      prz = f4_add(prz, f4_mul(r, z));
     }
     warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
     __syncthreads();
@@ -300,13 +293,11 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     rz = rzn;
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
-      if (act[m]) {
-        const int row = tid + T * m;
-        const float4 p = p_s[row];
-        const float4 z = zz[m];
-        p_s[row] = make_float4(fmaf(p.x, beta.x, z.x), fmaf(p.y, beta.y, z.y), fmaf(p.z, beta.z, z.z),
-                               fmaf(p.w, beta.w, z.w));
-      }
+      const int row = tid + T * m;
+      const float4 p = p_s[row];
+      const float4 z = zz[m];
+      p_s[row] = make_float4(fmaf(p.x, beta.x, z.x), fmaf(p.y, beta.y, z.y), fmaf(p.z, beta.z, z.z),
+                             fmaf(p.w, beta.w, z.w));
     }
     __syncthreads();
     ++it;
@@ -410,15 +401,25 @@ template <int TPT, int KQ, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.N, kq = P.kq;
-  float4* p_s = reinterpret_cast<float4*>(smem_raw);                   // [N]
-  float4* w_s = p_s + N;                                                // [kq][N]
-  float4* red = w_s + (size_t)N * kq;                                   // 3 x RED_F4
-  ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 3 * RED_F4);        // [kq][N]
-  float* diag_s = reinterpret_cast<float*>(nbr_s + (size_t)N * kq);      // [N] operator diagonal
-  float* im_s = diag_s + N;                                             // [N] 1/(Mdiag + 1e-12)
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x;
+  const int Np = T * TPT;  // rows incl. pad rows (zero state / zero weights), see slab_solve
+  float4* p_s = reinterpret_cast<float4*>(smem_raw);                   // [Np]
+  float4* w_s = p_s + Np;                                               // [kq][Np]
+  float4* red = w_s + (size_t)Np * kq;                                  // 3 x RED_F4
+  ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 3 * RED_F4);        // [kq][Np]
+  float* diag_s = reinterpret_cast<float*>(nbr_s + (size_t)Np * kq);     // [Np] operator diagonal
+  float* im_s = diag_s + Np;                                            // [Np] 1/(Mdiag + 1e-12)
+  // pad rows are written here once and never again (staging and set-up touch rows < N only)
+  for (int e = tid; e < Np * kq; e += T) {
+    w_s[e] = f4_zero();
+    nbr_s[e] = make_ushort4(0, 0, 0, 0);
+  }
+  for (int e = tid; e < Np; e += T) {
+    p_s[e] = f4_zero();
+    diag_s[e] = 0.f;
+    im_s[e] = 0.f;
+  }
   bool act[TPT];
 #pragma unroll
   for (int m = 0; m < TPT; ++m) act[m] = (tid + T * m) < N;
@@ -451,10 +452,14 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
     {
       const uint4* src_w = reinterpret_cast<const uint4*>(P.pk_w) + b * N * kq;
       uint4* dst_w = reinterpret_cast<uint4*>(w_s);
-      for (int e = tid; e < N * kq; e += T) dst_w[e] = __ldg(src_w + e);
       const uint2* src_n = reinterpret_cast<const uint2*>(P.pk_nbr) + b * N * kq;
       uint2* dst_n = reinterpret_cast<uint2*>(nbr_s);
-      for (int e = tid; e < N * kq; e += T) dst_n[e] = __ldg(src_n + e);
+      for (int c = 0; c < kq; ++c) {
+        for (int e = tid; e < N; e += T) {
+          dst_w[c * Np + e] = __ldg(src_w + c * N + e);
+          dst_n[c * Np + e] = __ldg(src_n + c * N + e);
+        }
+      }
     }
     const float* Yb = P.Y + b * (int64_t)N * P.D;
     const float* Ub = (P.U_in ? P.U_in : P.Y) + b * (int64_t)N * P.D;
@@ -502,7 +507,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
                                   __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w)));
           }
         }
-        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, N, kq, p_s,
+        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, Np, kq, p_s,
                                               gb ? diag_s : nullptr, gb ? im_s : nullptr, nbr_s, w_s, red,
                                               act, &rr, share_r0 ? scr_acc : nullptr, nullptr);
         if (Uo != nullptr) {
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
                 __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
           }
         }
-        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, N, kq, p_s,
+        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, Np, kq, p_s,
                                               gb ? diag_s : nullptr, gb ? im_s : nullptr, nbr_s, w_s, red,
                                               act, &rr, nullptr, share_r0 ? scr_acc : nullptr);
         if (P.Ustar_out != nullptr) {
@@ -613,7 +618,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
               const int row = tid + T * m;
-              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, N, kq, gb ? diag_s[row] : c.diag_u, c.offc);
+              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, Np, kq, gb ? diag_s[row] : c.diag_u, c.offc);
               part = f4_add(part, f4_mul(p_s[row], a));
             }
           }
@@ -697,7 +702,9 @@ static int threads_for(int64_t N, int tpt) {
 }
 static size_t batched_smem(int64_t N, int k) {
   const int kp = (k + 3) / 4 * 4;
-  return (size_t)N * 16 + (size_t)N * kp * 4 + 3 * RED_F4 * 16 + (size_t)N * kp * 2 + (size_t)N * 8;
+  const int tpt = tpt_for(N);
+  const size_t Np = (size_t)threads_for(N, tpt) * tpt;  // rows incl. pad rows
+  return Np * 16 + Np * kp * 4 + 3 * RED_F4 * 16 + Np * kp * 2 + Np * 8;
 }
 
 int batched_supported(int64_t N, int D, int k) {
