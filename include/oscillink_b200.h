@@ -44,6 +44,8 @@ extern "C" {
 #define OSC_KNN_AUTO 0
 #define OSC_KNN_SIMT 1 /* fp32 CUDA-core tile kernel (any shape) */
 #define OSC_KNN_TC 2   /* tcgen05 3xTF32 tensor-core kernel (sm_100a) */
+#define OSC_KNN_TC1 3  /* tcgen05 single-product TF32 kernel: a third of the tensor work, scores only \
+                          pre-select candidates (error bound OSC_KNN_EPS_TC1, wider candidate lists) */
 
 /* solve modes for osc_pcg_* / osc_batched_* */
 #define OSC_MODE_SETTLE 0     /* (I + dt M) X = U + dt RHS   lattice.py:170-192 */
@@ -94,7 +96,8 @@ int osc_device_info(int device, int* h_sm_count, int* h_smem_optin, int* h_cc);
  * Replaces oscillink/core/graph.py:29-62 (normalise, S = Yn Yn^T, diag = -inf, top-k). */
 
 /* Yn = Y / (||Y||_2 + 1e-12) row-wise (graph.py:35).  Yn_hi/Yn_lo (optional, may be NULL)
- * receive the TF32 split used by the tensor-core kernel: hi = tf32(Yn), lo = tf32(Yn - hi). */
+ * receive the TF32 split used by the tensor-core kernels: hi = tf32(Yn), lo = tf32(Yn - hi);
+ * OSC_KNN_TC1 reads hi only (pass Yn_lo = NULL). */
 int osc_normalize_rows(const float* Y, int64_t rows, int32_t D, float* Yn, float* Yn_hi,
                        float* Yn_lo, void* stream);
 
@@ -110,6 +113,11 @@ int osc_knn_candidates(const float* Yn_q, const float* Yn_all, const float* q_hi
                        void* stream);
 /* 1 if the tcgen05 engine covers (N, D, kc) on the current device */
 int osc_knn_tc_supported(int64_t N, int32_t D, int32_t kc);
+/* Resolve `flags` (OSC_KNN_*, AUTO included) for n_rows query rows against N columns into the
+ * engine that osc_knn_build would run, the candidate-list width kc that engine needs and the
+ * bound eps on |approximate - exact| to hand to osc_knn_rescore_checked.  Any output may be NULL. */
+int osc_knn_plan(int64_t n_rows, int64_t N, int32_t D, int32_t k, int32_t flags, int32_t* h_engine,
+                 int32_t* h_kc, float* h_eps);
 int osc_knn_candidates_workspace(int64_t batch, int64_t n_rows, int64_t N, int32_t D, int32_t kc,
                                  int32_t flags, size_t* h_bytes);
 
@@ -124,10 +132,16 @@ int osc_knn_rescore(const float* Yn_q, const float* Yn_all, int64_t batch, int64
  * A column outside the list scored <= a_min (smallest approximate score kept) in the approximate
  * pass, so it can only be a true top-k column if a_min + eps >= the exact k-th score; such rows are
  * recomputed exhaustively (all N columns, same fp64-accumulated dot, graph.py:46-52 ordering).
+ * The same bound prunes the work: cand_sim is sorted descending, k candidates score >= cand_sim[k-1]
+ * approximately, hence >= cand_sim[k-1] - eps exactly, so a candidate below cand_sim[k] - 2 eps can
+ * be neither a top-k column nor the (k+1)-th (the `gap` output) and its row is never fetched.
  * eps bounds |approximate - exact| of the candidate engine (OSC_KNN_EPS covers 3xTF32 with
  * truncating accumulation and the fp32 FMA engine).  *d_n_flagged (device int32) receives the
  * number of rows that took the exhaustive path.  row0 = global id of the first query row. */
 #define OSC_KNN_EPS 1e-5f
+/* single-product TF32: both operands rounded to 11 significant bits => |error| <= 2^-10 * sum|a_i b_i|
+ * <= 2^-10 for unit rows (Cauchy-Schwarz), plus the accumulation noise covered by OSC_KNN_EPS */
+#define OSC_KNN_EPS_TC1 1e-3f
 int osc_knn_rescore_workspace(int64_t batch, int64_t n_rows, size_t* h_bytes);
 int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
                             int64_t row0, int64_t N, int32_t D, const int32_t* cand_idx,

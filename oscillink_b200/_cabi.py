@@ -16,9 +16,10 @@ _lock = threading.Lock()
 _lib = None
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-KNN_AUTO, KNN_SIMT, KNN_TC = 0, 1, 2
+KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC1 = 0, 1, 2, 3
 MODE_SETTLE, MODE_STATIONARY = 0, 1
 KNN_EPS = 1e-5  # OSC_KNN_EPS
+KNN_EPS_TC1 = 1e-3  # OSC_KNN_EPS_TC1
 
 c_i32, c_i64, c_f32, c_f64, c_void_p, c_size_t = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_size_t
 
@@ -60,6 +61,7 @@ PROTOTYPES = {
     "osc_knn_candidates": (C.c_int, [c_void_p] * 6 + [c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32,
                                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "osc_knn_tc_supported": (C.c_int, [c_i64, c_i32, c_i32]),
+    "osc_knn_plan": (C.c_int, [c_i64, c_i64, c_i32, c_i32, c_i32, P(c_i32), P(c_i32), P(c_f32)]),
     "osc_knn_candidates_workspace": (C.c_int, [c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, P(c_size_t)]),
     "osc_knn_rescore": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_void_p, c_i32, c_i32,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -168,3 +170,10 @@ def check(rc: int, what: str = "") -> None:
 def ptr(t) -> int | None:
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def knn_plan(n_rows: int, N: int, D: int, k: int, flags: int) -> tuple[int, int, float]:
+    """(engine, candidate width kc, error bound eps) that `flags` resolves to -- osc_knn_plan."""
+    eng, kc, eps = c_i32(0), c_i32(0), c_f32(0.0)
+    check(load().osc_knn_plan(n_rows, N, D, k, flags, C.byref(eng), C.byref(kc), C.byref(eps)), "osc_knn_plan")
+    return eng.value, kc.value, eps.value

@@ -89,16 +89,14 @@ class BatchedLattices:
                                           self.nnz.data_ptr(), self.gap.data_ptr(), ws.data_ptr(),
                                           ws.numel(), self._stream()), "osc_knn_build")
             return
-        kc = min(k + 4, N - 1)
         rows = B * N
-        use_tc = (self._engine != _cabi.KNN_SIMT and bool(lib.osc_knn_tc_supported(N, D, kc))
-                  and (self._engine == _cabi.KNN_TC or N >= 256))
-        if self._engine == _cabi.KNN_TC and not use_tc:
-            raise _cabi.OscillinkNativeError("tensor-core kNN engine does not cover this shape")
-        self.engine_used = "tc" if use_tc else "simt"
+        eng, kc, eps = _cabi.knn_plan(N, N, D, k, self._engine)
+        use_tc = eng in (_cabi.KNN_TC, _cabi.KNN_TC1)
+        self.engine_used = {_cabi.KNN_SIMT: "simt", _cabi.KNN_TC: "tc", _cabi.KNN_TC1: "tc1"}[eng]
+        self.kc = kc
         Yn = torch.empty_like(self.Y)
         hi = torch.empty_like(self.Y) if use_tc else None
-        lo = torch.empty_like(self.Y) if use_tc else None
+        lo = torch.empty_like(self.Y) if eng == _cabi.KNN_TC else None
         cand_idx = torch.empty((B, N, kc), dtype=torch.int32, device=dev)
         cand_sim = torch.empty((B, N, kc), dtype=torch.float32, device=dev)
         top_idx = torch.empty((B, N, k), dtype=torch.int32, device=dev)
@@ -118,7 +116,7 @@ class BatchedLattices:
                                                           P(hi), P(lo), st))
         phase("knn_candidates", lambda: lib.osc_knn_candidates(
             Yn.data_ptr(), Yn.data_ptr(), P(hi), P(lo), P(hi), P(lo), B, N, 0, N, D, kc,
-            _cabi.KNN_TC if use_tc else _cabi.KNN_SIMT, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st))
+            eng, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st))
         # canonical re-scoring + completeness check of every candidate list (rows that cannot be proven
         # complete are recomputed exhaustively on device; n_exhaustive counts them)
         self.n_exhaustive = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -127,7 +125,7 @@ class BatchedLattices:
         rws = self._workspace(need.value)
         phase("knn_rescore", lambda: lib.osc_knn_rescore_checked(
             Yn.data_ptr(), Yn.data_ptr(), B, N, 0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
-            _cabi.KNN_EPS, top_idx.data_ptr(), top_sim.data_ptr(), self.gap.data_ptr(),
+            eps, top_idx.data_ptr(), top_sim.data_ptr(), self.gap.data_ptr(),
             self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st))
         phase("graph_assemble", lambda: lib.osc_graph_assemble(
             top_idx.data_ptr(), top_sim.data_ptr(), B, N, k, self.row_cap_val, self.nbr.data_ptr(),

@@ -191,7 +191,11 @@ __device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nb
 // One PCG solve for this CTA's slab (solver.py:15-37).  On exit st.X holds the iterate of the
 // returned iteration.  forced == 0: stop at the first iteration whose slab residual is <= tol
 // (or at max_iters); forced > 0: run exactly `forced` iterations.  *rr_out = max_c ||r_c||^2 there.
-template <int TPT, int KQ>
+//
+// GATES = false (no gates given, b == 1): the operator diagonal and the Jacobi preconditioner are
+// the same number for every row, so z = im_u * r and r.z = im_u * r.r -- the r.z reduction and the
+// z vector disappear (one 4-value reduction per phase instead of 4 + 8).
+template <int TPT, int KQ, int T, bool GATES>
 __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max_iters, int forced,
                           int N, int kq, float4* p_s, const float* diag_s, const float* im_s, const ushort4* nbr_s,
                           const float4* w_s, float4* red, const bool (&act)[TPT], float* rr_out,
@@ -200,7 +204,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   // acc_in  != nullptr: they are read back instead of gathering x0 again (same x0, same graph:
   //                     bit-identical to recomputing them).
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = blockDim.x, nw = T >> 5;
+  constexpr int nw = T >> 5;
   float4* redA = red;               // init r.z, then p.Ap
   float4* redB = red + RED_F4;      // r.r
   float4* redC = red + 2 * RED_F4;  // r.z'
@@ -213,12 +217,10 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   }
   __syncthreads();  // x0 visible; diag_s, im_s of this solve visible
   // ---- r0 = b - A x0 ; z0 ; rz
-  float4 z0[TPT];
   float4 part = f4_zero();
 #pragma unroll
   for (int m = 0; m < TPT; ++m) {
     const int row = tid + T * m;
-    const float imr = im_s ? im_s[row] : c.im_u;
     float4 g;
     if (acc_in != nullptr) {
       g = act[m] ? acc_in[row] : f4_zero();
@@ -226,18 +228,27 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
       g = gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq);
       if (acc_out != nullptr && act[m]) acc_out[row] = g;
     }
-    const float4 a = combine_row(st.X[m], g, diag_s ? diag_s[row] : c.diag_u, c.offc);
+    const float4 a = combine_row(st.X[m], g, GATES ? diag_s[row] : c.diag_u, c.offc);
     float4 r = st.R[m];
     r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
     st.R[m] = r;
-    z0[m] = make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr);
-    part = f4_add(part, f4_mul(r, z0[m]));
+    if (GATES) {
+      const float imr = im_s[row];
+      part = f4_add(part, f4_mul(r, make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr)));
+    } else {
+      part = f4_add(part, f4_mul(r, r));
+    }
   }
   warp_reduce4(part, redA + warp, lane);
   __syncthreads();  // also: every gather of x0 has completed
   float rz = block_total_c(redA, nw, lane);  // component lane&3
+  if (!GATES) rz *= c.im_u;
 #pragma unroll
-  for (int m = 0; m < TPT; ++m) p_s[tid + T * m] = z0[m];
+  for (int m = 0; m < TPT; ++m) {
+    const float imr = GATES ? im_s[tid + T * m] : c.im_u;
+    const float4 r = st.R[m];
+    p_s[tid + T * m] = make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr);  // p0 = z0
+  }
   __syncthreads();
 
   int it = 1;
@@ -250,7 +261,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
       const int row = tid + T * m;
       const float4 own = p_s[row];
       st.AP[m] = combine_row(own, gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq),
-                             diag_s ? diag_s[row] : c.diag_u, c.offc);
+                             GATES ? diag_s[row] : c.diag_u, c.offc);
       part = f4_add(part, f4_mul(own, st.AP[m]));
     }
     warp_reduce4(part, redA + warp, lane);
@@ -259,7 +270,6 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     const float4 alpha = bcast4(__fdiv_rn(rz, pap + 1e-18f));
     // ---- C: x, r update; rr and rz'
     float4 prr = f4_zero(), prz = f4_zero();
-    float4 zz[TPT];
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
@@ -272,32 +282,41 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
                       fmaf(-ap.w, alpha.w, r.w));
       st.X[m] = x;
       st.R[m] = r;
-      const float im = im_s ? im_s[row] : c.im_u;
-      const float4 z = make_float4(r.x * im, r.y * im, r.z * im, r.w * im);
-      zz[m] = z;
       prr = f4_add(prr, f4_mul(r, r));
-      prz = f4_add(prz, f4_mul(r, z));
+      if (GATES) {
+        const float im = im_s[row];
+        prz = f4_add(prz, f4_mul(r, make_float4(r.x * im, r.y * im, r.z * im, r.w * im)));
+      }
     }
-    warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
-    __syncthreads();
-    const float rr = block_total_c(redB, nw, lane);
-    const float rzn = block_total_c(redC, nw, lane);
+    float rr, rzn;
+    if (GATES) {
+      warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
+      __syncthreads();
+      rr = block_total_c(redB, nw, lane);
+      rzn = block_total_c(redC, nw, lane);
+    } else {
+      warp_reduce4(prr, redB + warp, lane);
+      __syncthreads();
+      rr = block_total_c(redB, nw, lane);
+      rzn = rr * c.im_u;
+    }
     mx = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     // identical in every thread (same summation order) -> uniform branch
     const bool stop = forced > 0 ? (it >= forced)
                                  : ((double)__fsqrt_rn(mx) <= tol || it >= max_iters);
     if (stop) break;
-    // ---- E: p = z + beta p
+    // ---- E: p = z + beta p   (z = r / (Mdiag + 1e-12), recomputed from r: one FMUL per element)
     const float4 beta = bcast4(__fdiv_rn(rzn, rz + 1e-18f));
     rz = rzn;
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
+      const float im = GATES ? im_s[row] : c.im_u;
       const float4 p = p_s[row];
-      const float4 z = zz[m];
-      p_s[row] = make_float4(fmaf(p.x, beta.x, z.x), fmaf(p.y, beta.y, z.y), fmaf(p.z, beta.z, z.z),
-                             fmaf(p.w, beta.w, z.w));
+      const float4 r = st.R[m];
+      p_s[row] = make_float4(fmaf(p.x, beta.x, r.x * im), fmaf(p.y, beta.y, r.y * im),
+                             fmaf(p.z, beta.z, r.z * im), fmaf(p.w, beta.w, r.w * im));
     }
     __syncthreads();
     ++it;
@@ -397,19 +416,24 @@ batched_pack_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ W
   }
 }
 
-template <int TPT, int KQ, int MAXT, int MINB>
+template <int TPT, int KQ, int MAXT, int MINB, bool GATES>
 __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.N, kq = P.kq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = blockDim.x;
-  const int Np = T * TPT;  // rows incl. pad rows (zero state / zero weights), see slab_solve
-  float4* p_s = reinterpret_cast<float4*>(smem_raw);                   // [Np]
-  float4* w_s = p_s + Np;                                               // [kq][Np]
+  // the block size is the template's MAXT: every row address is tid*16 + an immediate
+  constexpr int T = MAXT;
+  constexpr int Np = T * TPT;  // rows incl. pad rows (zero state / zero weights), see slab_solve
+  // p lives in STATIC shared memory: its address is a link-time constant, so a gather is
+  // LDS.128 [offset + imm] straight from the packed u16 byte offset (no address arithmetic)
+  __shared__ __align__(16) float4 p_static[MAXT * TPT];
+  float4* p_s = p_static;                                               // [Np]
+  float4* w_s = reinterpret_cast<float4*>(smem_raw);                    // [kq][Np]
   float4* red = w_s + (size_t)Np * kq;                                  // 3 x RED_F4
   ushort4* nbr_s = reinterpret_cast<ushort4*>(red + 3 * RED_F4);        // [kq][Np]
-  float* diag_s = reinterpret_cast<float*>(nbr_s + (size_t)Np * kq);     // [Np] operator diagonal
-  float* im_s = diag_s + Np;                                            // [Np] 1/(Mdiag + 1e-12)
+  // with gates: [Np] operator diagonal and [Np] 1/(Mdiag + 1e-12) (not allocated otherwise)
+  float* diag_s = reinterpret_cast<float*>(nbr_s + (size_t)Np * kq);
+  float* im_s = diag_s + Np;
   // pad rows are written here once and never again (staging and set-up touch rows < N only)
   for (int e = tid; e < Np * kq; e += T) {
     w_s[e] = f4_zero();
@@ -417,8 +441,10 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
   }
   for (int e = tid; e < Np; e += T) {
     p_s[e] = f4_zero();
-    diag_s[e] = 0.f;
-    im_s[e] = 0.f;
+    if (GATES) {
+      diag_s[e] = 0.f;
+      im_s[e] = 0.f;
+    }
   }
   bool act[TPT];
 #pragma unroll
@@ -464,7 +490,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
     const float* Yb = P.Y + b * (int64_t)N * P.D;
     const float* Ub = (P.U_in ? P.U_in : P.Y) + b * (int64_t)N * P.D;
     float* Uo = P.U_out ? P.U_out + b * (int64_t)N * P.D : nullptr;
-    const float* gb = P.gates ? P.gates + b * N : nullptr;
+    const float* gb = GATES ? P.gates + b * N : nullptr;
 
     for (int s = s0; s < s1; ++s) {
       const int col = s * SC;
@@ -482,7 +508,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         c.diag_u = c.diag0 + c.diag1 * 1.0f;
         c.im_u = __fdiv_rn(1.0f, md_of(c, 1.0f) + 1e-12f);
         __syncthreads();  // previous solve's readers of diag_s, im_s, p_s are done
-        if (gb != nullptr) {
+        if (GATES) {
           for (int e = tid; e < N; e += T) {
             const float bq = gb[e];
             diag_s[e] = c.diag0 + c.diag1 * bq;
@@ -496,7 +522,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
             const int row = tid + T * m;
             const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
             const float4 u = P.U_in ? *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col) : y;
-            const float bq = gb ? gb[row] : 1.0f;
+            const float bq = GATES ? gb[row] : 1.0f;
             const float4 rhs = make_float4(
                 __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
                 __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
@@ -507,9 +533,9 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
                                   __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w)));
           }
         }
-        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_settle, P.max_iters_settle, Fs, Np, kq, p_s,
-                                              gb ? diag_s : nullptr, gb ? im_s : nullptr, nbr_s, w_s, red,
-                                              act, &rr, share_r0 ? scr_acc : nullptr, nullptr);
+        const int iters = slab_solve<TPT, KQ, T, GATES>(st, c, P.tol_settle, P.max_iters_settle, Fs, Np, kq,
+                                                     p_s, diag_s, im_s, nbr_s, w_s, red, act, &rr,
+                                                     share_r0 ? scr_acc : nullptr, nullptr);
         if (Uo != nullptr) {
 #pragma unroll
           for (int m = 0; m < TPT; ++m)
@@ -542,7 +568,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         c.diag_u = c.diag0 + c.diag1 * 1.0f;
         c.im_u = __fdiv_rn(1.0f, md_of(c, 1.0f) + 1e-12f);
         __syncthreads();  // the settle solve's readers of diag_s, im_s are done
-        if (gb != nullptr) {
+        if (GATES) {
           for (int e = tid; e < N; e += T) {
             const float bq = gb[e];
             diag_s[e] = c.diag0 + c.diag1 * bq;
@@ -555,7 +581,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           if (act[m]) {
             const int row = tid + T * m;
             const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
-            const float bq = gb ? gb[row] : 1.0f;
+            const float bq = GATES ? gb[row] : 1.0f;
             st.X[m] = y;
             st.R[m] = make_float4(
                 __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
@@ -564,9 +590,9 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
                 __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
           }
         }
-        const int iters = slab_solve<TPT, KQ>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, Np, kq, p_s,
-                                              gb ? diag_s : nullptr, gb ? im_s : nullptr, nbr_s, w_s, red,
-                                              act, &rr, nullptr, share_r0 ? scr_acc : nullptr);
+        const int iters = slab_solve<TPT, KQ, T, GATES>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, Np, kq,
+                                                     p_s, diag_s, im_s, nbr_s, w_s, red, act, &rr, nullptr,
+                                                     share_r0 ? scr_acc : nullptr);
         if (P.Ustar_out != nullptr) {
           float* So = P.Ustar_out + b * (int64_t)N * P.D;
 #pragma unroll
@@ -618,7 +644,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
               const int row = tid + T * m;
-              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, Np, kq, gb ? diag_s[row] : c.diag_u, c.offc);
+              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, Np, kq, GATES ? diag_s[row] : c.diag_u, c.offc);
               part = f4_add(part, f4_mul(p_s[row], a));
             }
           }
@@ -694,23 +720,25 @@ __global__ void batched_finalize_kernel(const int2* __restrict__ rec, const doub
 }
 
 // ================================================================= host side
-static int tpt_for(int64_t N) { return N <= 320 ? 1 : (N <= 640 ? 2 : 4); }
-static int threads_for(int64_t N, int tpt) {
-  int t = (int)((N + tpt - 1) / tpt);
-  t = (t + 31) / 32 * 32;
-  return t < 32 ? 32 : t;
+// kernel variant serving N rows: MAXT threads (the launch block size) x TPT rows per thread
+static int maxt_for(int64_t N) { return N <= 1280 ? 320 : 640; }
+static int tpt_for(int64_t N) {
+  const int t = maxt_for(N);
+  return (int)((N + t - 1) / t);  // 1..4
 }
-static size_t batched_smem(int64_t N, int k) {
+static size_t batched_smem(int64_t N, int k, bool gates) {
   const int kp = (k + 3) / 4 * 4;
-  const int tpt = tpt_for(N);
-  const size_t Np = (size_t)threads_for(N, tpt) * tpt;  // rows incl. pad rows
-  return Np * 16 + Np * kp * 4 + 3 * RED_F4 * 16 + Np * kp * 2 + Np * 8;
+  const size_t Np = (size_t)maxt_for(N) * tpt_for(N);  // rows incl. pad rows
+  return Np * kp * 4 + 3 * RED_F4 * 16 + Np * kp * 2 + (gates ? Np * 8 : 0);  // + p in static shared memory
 }
+
+// static shared memory of the kernel variant that serves N (p_static[MAXT * TPT])
+static size_t batched_static_smem(int64_t N) { return (size_t)maxt_for(N) * tpt_for(N) * 16; }
 
 int batched_supported(int64_t N, int D, int k) {
   if (N < 1 || N > 2560) return 0;
   if (D % 4 != 0 || D < 4) return 0;
-  if (k < 1 || k > PK_MAXK || batched_smem(N, k) > 227 * 1024) return 0;
+  if (k < 1 || k > PK_MAXK || batched_smem(N, k, true) + batched_static_smem(N) > 227 * 1024) return 0;
   return 1;
 }
 
@@ -725,14 +753,18 @@ int batched_workspace(int64_t batch, int64_t N, int D, size_t* bytes) {
 }
 
 typedef void (*BatchedFn)(BatchedK);
-template <int TPT, int MAXT, int MINB>
-static BatchedFn pick_kq(int kq) {
+template <int TPT, int MAXT, int MINB, bool GATES>
+static BatchedFn pick_kq2(int kq) {
   switch (kq) {
-    case 1: return batched_settle_kernel<TPT, 1, MAXT, MINB>;
-    case 2: return batched_settle_kernel<TPT, 2, MAXT, MINB>;
-    case 3: return batched_settle_kernel<TPT, 3, MAXT, MINB>;
-    default: return batched_settle_kernel<TPT, 4, MAXT, MINB>;
+    case 1: return batched_settle_kernel<TPT, 1, MAXT, MINB, GATES>;
+    case 2: return batched_settle_kernel<TPT, 2, MAXT, MINB, GATES>;
+    case 3: return batched_settle_kernel<TPT, 3, MAXT, MINB, GATES>;
+    default: return batched_settle_kernel<TPT, 4, MAXT, MINB, GATES>;
   }
+}
+template <int TPT, int MAXT, int MINB>
+static BatchedFn pick_kq(int kq, bool gates) {
+  return gates ? pick_kq2<TPT, MAXT, MINB, true>(kq) : pick_kq2<TPT, MAXT, MINB, false>(kq);
 }
 
 int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batched_args_t* a,
@@ -793,14 +825,18 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   P.tol_settle = a->tol_settle; P.tol_ustar = a->tol_ustar;
   P.max_iters_settle = a->max_iters_settle; P.max_iters_ustar = a->max_iters_ustar;
 
-  const size_t smem = batched_smem(N, g->k);
+  const bool gates = a->gates != nullptr;
+  const size_t smem = batched_smem(N, g->k, gates);
   const int tpt = tpt_for(N);
-  const int threads = threads_for(N, tpt);
+  const int threads = maxt_for(N);
   BatchedFn fn;
-  if (tpt == 1) fn = pick_kq<1, 320, 2>(kq);
-  else if (tpt == 2) fn = pick_kq<2, 320, 2>(kq);
-  else if (threads <= 320) fn = pick_kq<4, 320, 2>(kq);
-  else fn = pick_kq<4, 640, 1>(kq);
+  if (threads == 640) {
+    if (tpt <= 3) fn = pick_kq<3, 640, 1>(kq, gates);
+    else fn = pick_kq<4, 640, 1>(kq, gates);
+  } else if (tpt == 1) fn = pick_kq<1, 320, 2>(kq, gates);
+  else if (tpt == 2) fn = pick_kq<2, 320, 2>(kq, gates);
+  else if (tpt == 3) fn = pick_kq<3, 320, 2>(kq, gates);
+  else fn = pick_kq<4, 320, 2>(kq, gates);
   OSC_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, threads, smem));

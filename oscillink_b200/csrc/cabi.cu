@@ -39,9 +39,10 @@ int launch_normalize(const float*, int64_t, int, float*, float*, float*, cudaStr
 int launch_knn_simt(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, int, int32_t*,
                     float*, cudaStream_t);
 int knn_tc_supported(int64_t N, int D, int kc);
+int knn_tc1_supported(int64_t n_rows, int64_t N, int D, int kc);
 int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
                   int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
-                  int32_t* cand_idx, float* cand_sim, cudaStream_t st);
+                  int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st);
 int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, const int32_t*,
                    const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t);
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
@@ -83,22 +84,44 @@ int batched_workspace(int64_t, int64_t, int, size_t*);
 int batched_settle(const osc_graph_t*, const osc_params_t*, const osc_batched_args_t*, void*, size_t,
                    cudaStream_t);
 
-static int candidate_width(int64_t N, int k) {
-  // k + 4 spare candidates so that 3xTF32 / fp32 rounding noise (~1e-7) cannot push a true
-  // top-k column out of the candidate list (DESIGN.md "near-ties")
+// Candidate-list width per engine.
+//  3xTF32 / fp32 FMA engines (error ~1e-6): k + 4 spare candidates.
+//  single-product TF32 engine (error bound 2^-10): the list must reach ~1e-3 below the k-th
+//  score for the completeness check to pass without the exhaustive path -- about as many spare
+//  candidates as neighbours; the register top-k exists for 16 / 24 / 32 entries, so the whole
+//  template width is used (k <= 8: 16, k <= 12: 24, else 32).
+static int candidate_width(int64_t N, int k, int eng) {
   int64_t kc = (int64_t)k + 4;
+  if (eng == OSC_KNN_TC1) {
+    const int want = 2 * k < 16 ? 16 : 2 * k;
+    const int64_t wide = want <= 16 ? 16 : (want <= 24 ? 24 : 32);
+    if (wide > kc) kc = wide;
+  }
   if (kc > N - 1) kc = N - 1;
   if (kc < 1) kc = 1;
   return (int)kc;
 }
 
-static int pick_engine(int flags, int64_t N, int D, int kc) {
+static float engine_eps(int eng) { return eng == OSC_KNN_TC1 ? OSC_KNN_EPS_TC1 : OSC_KNN_EPS; }
+
+// AUTO resolves to the single-product engine only when OSC_KNN_AUTO=tc1 is set (A/B switch)
+static bool auto_prefers_tc1() {
+  const char* e = getenv("OSC_KNN_AUTO");
+  return e != nullptr && (strcmp(e, "tc1") == 0 || strcmp(e, "TC1") == 0);
+}
+
+// engine for `n_rows` query rows against N columns; -1: the requested engine does not cover the shape
+static int pick_engine(int flags, int64_t n_rows, int64_t N, int D, int k) {
   const int want = flags & 3;
   if (want == OSC_KNN_SIMT) return OSC_KNN_SIMT;
-  const int ok = knn_tc_supported(N, D, kc);
-  if (want == OSC_KNN_TC) return ok ? OSC_KNN_TC : -1;
+  const int ok3 = knn_tc_supported(N, D, candidate_width(N, k, OSC_KNN_TC));
+  const int ok1 = knn_tc1_supported(n_rows, N, D, candidate_width(N, k, OSC_KNN_TC1));
+  if (want == OSC_KNN_TC) return ok3 ? OSC_KNN_TC : -1;
+  if (want == OSC_KNN_TC1) return ok1 ? OSC_KNN_TC1 : -1;
   // AUTO: 128x256 tensor tiles only pay off once a lattice fills a few of them
-  return (ok && N >= 256) ? OSC_KNN_TC : OSC_KNN_SIMT;
+  if (N < 256) return OSC_KNN_SIMT;
+  if (ok1 && k <= 16 && auto_prefers_tc1()) return OSC_KNN_TC1;
+  return ok3 ? OSC_KNN_TC : OSC_KNN_SIMT;
 }
 
 }  // namespace osc
@@ -125,11 +148,22 @@ int osc_device_info(int device, int* h_sm_count, int* h_smem_optin, int* h_cc) {
 int osc_normalize_rows(const float* Y, int64_t rows, int32_t D, float* Yn, float* Yn_hi, float* Yn_lo,
                        void* stream) {
   OSC_REQUIRE(Y != nullptr && Yn != nullptr && rows >= 0 && D >= 1, "normalize_rows: bad argument");
-  OSC_REQUIRE((Yn_hi == nullptr) == (Yn_lo == nullptr), "normalize_rows: hi/lo must come together");
+  OSC_REQUIRE(Yn_lo == nullptr || Yn_hi != nullptr, "normalize_rows: lo without hi");
   return launch_normalize(Y, rows, D, Yn, Yn_hi, Yn_lo, (cudaStream_t)stream);
 }
 
 int osc_knn_tc_supported(int64_t N, int32_t D, int32_t kc) { return knn_tc_supported(N, D, kc); }
+
+int osc_knn_plan(int64_t n_rows, int64_t N, int32_t D, int32_t k, int32_t flags, int32_t* h_engine,
+                 int32_t* h_kc, float* h_eps) {
+  OSC_REQUIRE(n_rows >= 1 && N >= 2 && D >= 1 && k >= 1 && k <= N - 1, "knn_plan: bad shape");
+  const int eng = pick_engine(flags, n_rows, N, D, k);
+  if (eng < 0) return fail(OSC_ERR_UNSUPPORTED, "knn_plan: tensor-core engine does not cover this shape");
+  if (h_engine) *h_engine = eng;
+  if (h_kc) *h_kc = candidate_width(N, k, eng);
+  if (h_eps) *h_eps = engine_eps(eng);
+  return OSC_OK;
+}
 
 int osc_knn_candidates_workspace(int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, size_t* h_bytes) {
   if (h_bytes) *h_bytes = 256;
@@ -145,12 +179,22 @@ int osc_knn_candidates(const float* Yn_q, const float* Yn_all, const float* q_hi
   OSC_REQUIRE(batch <= 65535, "knn_candidates: batch > 65535 (split the batch)");
   OSC_REQUIRE(cand_idx != nullptr && cand_sim != nullptr, "knn_candidates: NULL output");
   if (batch == 0 || n_rows == 0) return OSC_OK;
-  const int eng = pick_engine(flags, N, D, kc);
-  if (eng < 0) return fail(OSC_ERR_UNSUPPORTED, "knn_candidates: tensor-core engine does not cover this shape");
+  // The caller fixed kc (and the eps it will hand to the checked re-scoring), so AUTO never picks
+  // the single-product engine here: that one is entered on explicit request only (osc_knn_plan).
+  int eng = flags & 3;
+  if (eng == OSC_KNN_AUTO) eng = (N >= 256 && knn_tc_supported(N, D, kc)) ? OSC_KNN_TC : OSC_KNN_SIMT;
+  if ((eng == OSC_KNN_TC && !knn_tc_supported(N, D, kc)) ||
+      (eng == OSC_KNN_TC1 && !knn_tc1_supported(n_rows, N, D, kc)))
+    return fail(OSC_ERR_UNSUPPORTED, "knn_candidates: tensor-core engine does not cover this shape");
+  if (eng == OSC_KNN_TC1) {
+    OSC_REQUIRE(q_hi && all_hi, "knn_candidates: TC1 engine needs the tf32-rounded rows (hi)");
+    return launch_knn_tc(q_hi, nullptr, all_hi, nullptr, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
+                         true, (cudaStream_t)stream);
+  }
   if (eng == OSC_KNN_TC) {
     OSC_REQUIRE(q_hi && q_lo && all_hi && all_lo, "knn_candidates: TC engine needs the hi/lo split");
     return launch_knn_tc(q_hi, q_lo, all_hi, all_lo, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
-                         (cudaStream_t)stream);
+                         false, (cudaStream_t)stream);
   }
   OSC_REQUIRE(Yn_q != nullptr && Yn_all != nullptr, "knn_candidates: NULL input");
   return launch_knn_simt(Yn_q, Yn_all, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
@@ -212,11 +256,13 @@ int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int3
     *h_bytes = 256;
     return OSC_OK;
   }
-  const int kc = candidate_width(N, k);
-  const int eng = pick_engine(flags, N, D, kc);
+  int eng = pick_engine(flags, N, N, D, k);
+  if (eng < 0) eng = OSC_KNN_TC;  // osc_knn_build reports the error; size for the larger layout
+  const int kc = candidate_width(N, k, eng);
   const size_t rows = (size_t)batch * N;
-  size_t b = align_up(rows * D * sizeof(float));                      // Yn
+  size_t b = align_up(rows * D * sizeof(float));                       // Yn
   if (eng == OSC_KNN_TC) b += 2 * align_up(rows * D * sizeof(float));  // hi, lo
+  if (eng == OSC_KNN_TC1) b += align_up(rows * D * sizeof(float));     // hi
   b += align_up(rows * kc * sizeof(int32_t)) + align_up(rows * kc * sizeof(float));  // candidates
   b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
   b += align_up(rows * sizeof(float));                                               // cap scale
@@ -252,16 +298,14 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   int rc = osc_knn_build_workspace(batch, N, D, k, flags, &need);
   if (rc) return rc;
   if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
-  const int kc = candidate_width(N, k);
-  const int eng = pick_engine(flags, N, D, kc);
+  const int eng = pick_engine(flags, N, N, D, k);
   if (eng < 0) return fail(OSC_ERR_UNSUPPORTED, "knn_build: tensor-core engine does not cover this shape");
+  const int kc = candidate_width(N, k, eng);
   Arena ar(workspace, ws_bytes);
   float* Yn = ar.take<float>(rows * D);
   float *hi = nullptr, *lo = nullptr;
-  if (eng == OSC_KNN_TC) {
-    hi = ar.take<float>(rows * D);
-    lo = ar.take<float>(rows * D);
-  }
+  if (eng == OSC_KNN_TC || eng == OSC_KNN_TC1) hi = ar.take<float>(rows * D);
+  if (eng == OSC_KNN_TC) lo = ar.take<float>(rows * D);
   int32_t* cand_idx = ar.take<int32_t>(rows * kc);
   float* cand_sim = ar.take<float>(rows * kc);
   int32_t* top_idx = ar.take<int32_t>(rows * k);
@@ -276,8 +320,8 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
     return rc;
   OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * rows * k, st));
   OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * rows * k, st));
-  if ((rc = launch_rescore(Yn, Yn, batch, N, 0, N, D, cand_idx, cand_sim, kc, k, OSC_KNN_EPS, top_idx, top_sim,
-                           gap, flagged, n_flagged, st)))
+  if ((rc = launch_rescore(Yn, Yn, batch, N, 0, N, D, cand_idx, cand_sim, kc, k, engine_eps(eng), top_idx,
+                           top_sim, gap, flagged, n_flagged, st)))
     return rc;
   return launch_assemble(top_idx, top_sim, batch, N, k, row_cap, nbr, A, W, deg, sqrt_deg, nnz, cscale, st);
 }

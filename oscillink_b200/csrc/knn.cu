@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
     if (hi != nullptr) {
       const float h = to_tf32(v);
       hi[row * D + d] = h;
-      lo[row * D + d] = to_tf32(v - h);
+      if (lo != nullptr) lo[row * D + d] = to_tf32(v - h);
     }
   }
 }
@@ -164,17 +164,33 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
   const float* yi = Yq + (b * n_rows + r) * D;
   const float* all = Yall + b * N * D;
   const int32_t* ci = cand_idx + (b * n_rows + r) * kc;
+  // Pruning with the engine's error bound (cand_sim sorted descending): k candidates score at least
+  // cs[k-1] approximately, so the exact k-th score is >= cs[k-1] - eps, and likewise the exact
+  // (k+1)-th is >= cs[k] - eps; a candidate below cs[k] - 2 eps is exactly below both and is dropped
+  // without fetching its row.
+  const float* cs = cand_sim != nullptr ? cand_sim + (b * n_rows + r) * kc : nullptr;
+  int n_keep = kc;
+  if (cs != nullptr && kc > k) {
+    const float thr = cs[k] - 2.0f * eps;
+    int cnt = 0;
+    for (int c = lane; c < kc; c += 32) cnt += (cs[c] >= thr) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    n_keep = cnt < k + 1 ? k + 1 : cnt;  // a prefix of the sorted list; -inf tails carry idx -1
+    if (n_keep > kc) n_keep = kc;
+  }
+  for (int c = n_keep + lane; c < kc; c += 32) sj[c] = -1;
   // Four candidates at a time: their row fetches are independent, so a lane keeps up to 4 x D/128
   // 16-byte loads in flight (the pass is bound by L2/HBM latency, not by the fp64 FMAs).  Lane l
   // owns elements {4l..4l+3} + 128 t of every row, for (i,j) and (j,i) alike: S stays symmetric.
   const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(yi) | reinterpret_cast<uintptr_t>(all)) % 16 == 0);
-  for (int c0 = 0; c0 < kc; c0 += 4) {
+  for (int c0 = 0; c0 < n_keep; c0 += 4) {
     int jc[4];
     const float* yj[4];
     double acc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      jc[u] = (c0 + u < kc) ? ci[c0 + u] : -1;
+      jc[u] = (c0 + u < n_keep) ? ci[c0 + u] : -1;
       yj[u] = all + (int64_t)(jc[u] >= 0 ? jc[u] : 0) * D;
       acc[u] = 0.0;
     }
@@ -183,7 +199,8 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
         const float4 q = *reinterpret_cast<const float4*>(yi + d);
         float4 x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(yj[u] + d);
+        for (int u = 0; u < 4; ++u)
+          x[u] = jc[u] >= 0 ? *reinterpret_cast<const float4*>(yj[u] + d) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           acc[u] = fma((double)q.x, (double)x[u].x, acc[u]);
@@ -196,13 +213,14 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
       for (int d = lane; d < D; d += 32) {
         const double q = (double)yi[d];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fma(q, (double)yj[u][d], acc[u]);
+        for (int u = 0; u < 4; ++u)
+          if (jc[u] >= 0) acc[u] = fma(q, (double)yj[u][d], acc[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const double t = warp_sum(acc[u]);
-      if (lane == 0 && c0 + u < kc) {
+      if (lane == 0 && c0 + u < n_keep) {
         sv[c0 + u] = jc[u] >= 0 ? (float)t : -INFINITY;
         sj[c0 + u] = jc[u];
       }
@@ -239,10 +257,9 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
   // a_min + eps exactly; it can only belong to the true top-k if that reaches the exact k-th
   // score.  Such rows (and rows with fewer than k valid candidates) are re-done exhaustively.
   if (cand_sim != nullptr && flagged != nullptr && (int64_t)kc < N - 1) {
-    const float* cs = cand_sim + (b * n_rows + r) * kc;
     float amin = INFINITY;
     for (int c = lane; c < kc; c += 32)
-      if (sj[c] >= 0) amin = fminf(amin, cs[c]);
+      if (ci[c] >= 0) amin = fminf(amin, cs[c]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off));
     // kth == +inf: fewer than k valid candidates

@@ -368,10 +368,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant
 //              their own TMEM half (128 lanes x 256 columns, double-buffered)
 //   tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogues of
 //   both CTAs arrive on the leader's "accumulator drained" barrier.
-constexpr int TC2_STAGES = 3;
+//
+// ONEPASS = true: the single-product engine (OSC_KNN_TC1).  Only the tf32-rounded operands are
+// staged and ONE MMA is issued per K=8 step (a third of the tensor work, half of the staging
+// traffic per k-block, twice the pipeline depth).  Its scores carry the full TF32 operand error
+// (<= 2^-10 for unit rows); they only pre-select candidates -- the final sets and weights come from
+// the exact re-scoring, and the completeness check uses that error as a rigorous bound.
 constexpr int TC2_HALF_BYTES = 128 * TC_BK * 4;                     // 128 rows x 32 floats
-constexpr int TC2_STAGE_BYTES = 4 * TC2_HALF_BYTES;                 // Ahi, Alo, Bhi(half), Blo(half)
-constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + TC_EPI_BYTES;
+template <bool ONEPASS>
+struct Tc2Cfg {
+  static constexpr int STAGES = ONEPASS ? 6 : 3;
+  static constexpr int STAGE_BYTES = (ONEPASS ? 2 : 4) * TC2_HALF_BYTES;  // Ahi [Alo] Bhi(half) [Blo(half)]
+};
+constexpr int TC2_SMEM = 3 * 4 * TC2_HALF_BYTES + 1024 + 256 + TC_EPI_BYTES;  // same for both configs
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -417,11 +426,13 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
       : "memory");
 }
 
-template <int KC>
+template <int KC, bool ONEPASS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                TcParams P) {
+  constexpr int TC2_STAGES = Tc2Cfg<ONEPASS>::STAGES;
+  constexpr int TC2_STAGE_BYTES = Tc2Cfg<ONEPASS>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -474,10 +485,15 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             const uint32_t sb = base + p.stage * TC2_STAGE_BYTES;
             const uint32_t fb = mapa_rank(full0 + 8 * p.stage, 0);   // the leader's full barrier
             if (leader) mbar_expect_tx(full0 + 8 * p.stage, 2 * TC2_STAGE_BYTES);
-            tma_load_3d_pair(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
-            tma_load_3d_pair(&tm_q_lo, sb + TC2_HALF_BYTES, fb, kb * TC_BK, m0, b);
-            tma_load_3d_pair(&tm_a_hi, sb + 2 * TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
-            tma_load_3d_pair(&tm_a_lo, sb + 3 * TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+            if constexpr (ONEPASS) {
+              tma_load_3d_pair(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
+              tma_load_3d_pair(&tm_a_hi, sb + TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+            } else {
+              tma_load_3d_pair(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
+              tma_load_3d_pair(&tm_q_lo, sb + TC2_HALF_BYTES, fb, kb * TC_BK, m0, b);
+              tma_load_3d_pair(&tm_a_hi, sb + 2 * TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+              tma_load_3d_pair(&tm_a_lo, sb + 3 * TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+            }
             p.advance(TC2_STAGES);
           }
         }
@@ -500,14 +516,23 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             tc_fence_after();
             if (lane == 0) {
               const uint32_t sb = base + p.stage * TC2_STAGE_BYTES;
-              const uint64_t ah = umma_desc(sb), al = umma_desc(sb + TC2_HALF_BYTES),
-                             bh = umma_desc(sb + 2 * TC2_HALF_BYTES), bl = umma_desc(sb + 3 * TC2_HALF_BYTES);
+              if constexpr (ONEPASS) {
+                const uint64_t ah = umma_desc(sb), bh = umma_desc(sb + TC2_HALF_BYTES);
 #pragma unroll
-              for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                const uint64_t o = (uint64_t)((ks * 32) >> 4);
-                tc_mma_tf32_pair(tacc, al + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
-                tc_mma_tf32_pair(tacc, ah + o, bl + o, idesc, 1u);
-                tc_mma_tf32_pair(tacc, ah + o, bh + o, idesc, 1u);
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                  const uint64_t o = (uint64_t)((ks * 32) >> 4);
+                  tc_mma_tf32_pair(tacc, ah + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
+                }
+              } else {
+                const uint64_t ah = umma_desc(sb), al = umma_desc(sb + TC2_HALF_BYTES),
+                               bh = umma_desc(sb + 2 * TC2_HALF_BYTES), bl = umma_desc(sb + 3 * TC2_HALF_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                  const uint64_t o = (uint64_t)((ks * 32) >> 4);
+                  tc_mma_tf32_pair(tacc, al + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
+                  tc_mma_tf32_pair(tacc, ah + o, bl + o, idesc, 1u);
+                  tc_mma_tf32_pair(tacc, ah + o, bh + o, idesc, 1u);
+                }
               }
               tc_commit_pair(empty0 + 8 * p.stage);  // stage free in BOTH CTAs once these MMAs retire
               if (kb == P.k_blocks - 1) tc_commit_pair(tfull0 + 8 * acc.stage);
@@ -617,17 +642,28 @@ int knn_tc_supported(int64_t N, int D, int kc) {
   return mj == 10 ? 1 : 0;
 }
 
+// the single-product engine exists only as the 2-CTA kernel: it needs more than one 128-row panel
+int knn_tc1_supported(int64_t n_rows, int64_t N, int D, int kc) {
+  return knn_tc_supported(N, D, kc) && n_rows > TC_BM && sm_count() >= 2;
+}
+
 int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
                   int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
-                  int32_t* cand_idx, float* cand_sim, cudaStream_t st) {
+                  int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st) {
   if (!knn_tc_supported(N, D, kc)) return fail(OSC_ERR_UNSUPPORTED, "knn_tc: shape not covered");
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (onepass) {  // the lo parts are not read (the caller may pass NULL)
+    OSC_REQUIRE(knn_tc1_supported(n_rows, N, D, kc), "knn_tc1: needs more than 128 query rows");
+    q_lo = q_hi;
+    all_lo = all_hi;
+  }
   OSC_REQUIRE(a16(q_hi) && a16(q_lo) && a16(all_hi) && a16(all_lo), "knn_tc: operands must be 16 B aligned");
   const int64_t sms = sm_count();
   bool pair = n_rows > TC_BM && sms >= 2;
+  if (onepass) pair = true;
   {
     const char* e = getenv("OSC_KNN_TC_PAIR");  // dev-only A/B switch: 0 = one CTA per tile
-    if (e) pair = pair && atoi(e) != 0;
+    if (e && !onepass) pair = pair && atoi(e) != 0;
   }
   CUtensorMap mqh, mql, mah, mal;
   int rc;
@@ -652,16 +688,21 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
     int64_t pairs = sms / 2;
     if (P.total_work < pairs) pairs = P.total_work;
     const unsigned grid = (unsigned)(2 * pairs);
-#define OSC_TC2_LAUNCH(K)                                                                                  \
+#define OSC_TC2_LAUNCH(K, OP)                                                                              \
   do {                                                                                                     \
-    OSC_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM)); \
-    knn_tc2_kernel<K><<<grid, TC_THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);                           \
+    OSC_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<K, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                  TC2_SMEM));                                                              \
+    knn_tc2_kernel<K, OP><<<grid, TC_THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);                        \
   } while (0)
-    if (kc <= 8) OSC_TC2_LAUNCH(8);
-    else if (kc <= 12) OSC_TC2_LAUNCH(12);
-    else if (kc <= 16) OSC_TC2_LAUNCH(16);
-    else if (kc <= 24) OSC_TC2_LAUNCH(24);
-    else OSC_TC2_LAUNCH(32);
+    if (onepass) {
+      if (kc <= 16) OSC_TC2_LAUNCH(16, true);
+      else if (kc <= 24) OSC_TC2_LAUNCH(24, true);
+      else OSC_TC2_LAUNCH(32, true);
+    } else if (kc <= 8) OSC_TC2_LAUNCH(8, false);
+    else if (kc <= 12) OSC_TC2_LAUNCH(12, false);
+    else if (kc <= 16) OSC_TC2_LAUNCH(16, false);
+    else if (kc <= 24) OSC_TC2_LAUNCH(24, false);
+    else OSC_TC2_LAUNCH(32, false);
 #undef OSC_TC2_LAUNCH
     OSC_LAUNCH_CHECK("knn_tc2_kernel");
     return OSC_OK;

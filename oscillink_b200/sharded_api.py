@@ -402,12 +402,12 @@ class ShardedLattice:
         sd = torch.full((N,), 1e-6, dtype=torch.float32, device=dev)
         self.nnz = torch.zeros(1, dtype=torch.int64, device=dev)
         if N >= 2:
-            kc = min(k + 4, N - 1)
-            use_tc = (self._engine != cabi.KNN_SIMT and bool(lib.osc_knn_tc_supported(N, D, kc))
-                      and (self._engine == cabi.KNN_TC or N >= 256))
+            eng, kc, eps = cabi.knn_plan(max(self.n_local, 1), N, D, k, self._engine)
+            use_tc = eng in (cabi.KNN_TC, cabi.KNN_TC1)
+            self.engine_used = {cabi.KNN_SIMT: "simt", cabi.KNN_TC: "tc", cabi.KNN_TC1: "tc1"}[eng]
             Yn = torch.empty_like(Y_all)
             hi = torch.empty_like(Y_all) if use_tc else None
-            lo = torch.empty_like(Y_all) if use_tc else None
+            lo = torch.empty_like(Y_all) if eng == cabi.KNN_TC else None
             P = cabi.ptr
             cabi.check(lib.osc_normalize_rows(Y_all.data_ptr(), N, D, Yn.data_ptr(), P(hi), P(lo), st))
             nl, r0 = self.n_local, self.row0
@@ -421,15 +421,14 @@ class ShardedLattice:
                 q = lambda t: None if t is None else t.data_ptr() + off  # noqa: E731
                 cabi.check(lib.osc_knn_candidates(
                     q(Yn), Yn.data_ptr(), q(hi), q(lo), P(hi), P(lo), 1, nl, r0, N, D, kc,
-                    cabi.KNN_TC if use_tc else cabi.KNN_SIMT, cand_idx.data_ptr(), cand_sim.data_ptr(),
-                    None, 0, st), "osc_knn_candidates")
+                    eng, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st), "osc_knn_candidates")
                 self.n_exhaustive = torch.zeros(1, dtype=torch.int32, device=dev)
                 need = C.c_size_t(0)
                 cabi.check(lib.osc_knn_rescore_workspace(1, nl, C.byref(need)))
                 rws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
                 cabi.check(lib.osc_knn_rescore_checked(
                     q(Yn), Yn.data_ptr(), 1, nl, r0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
-                    cabi.KNN_EPS, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
+                    eps, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
                     self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st),
                     "osc_knn_rescore_checked")
             self.gap_local = gap[:nl]

@@ -272,7 +272,11 @@ def test_tc_and_simt_engines_build_identical_graphs(shape):
     gen.manual_seed(N + D)
     Y = torch.randn((B, N, D), generator=gen, device=dev)
     res = {}
-    for name, eng in (("simt", _cabi.KNN_SIMT), ("tc", _cabi.KNN_TC)):
+    engines = [("simt", _cabi.KNN_SIMT), ("tc", _cabi.KNN_TC)]
+    if N > 128:  # the single-product engine is a 2-CTA kernel: more than one 128-row panel
+        engines.append(("tc1", _cabi.KNN_TC1))
+        assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TC1)[2] == pytest.approx(1e-3)
+    for name, eng in engines:
         nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev)
         A = torch.empty((B, N, k), dtype=torch.float32, device=dev)
         W = torch.empty_like(A)
@@ -289,7 +293,63 @@ def test_tc_and_simt_engines_build_identical_graphs(shape):
                                       torch.cuda.current_stream().cuda_stream), name)
         torch.cuda.synchronize()
         res[name] = (nbr.cpu().numpy(), A.cpu().numpy(), W.cpu().numpy(), nnz.cpu().numpy())
-    for a, b in zip(res["simt"], res["tc"]):
+    for name, _ in engines[1:]:
+        for a, b in zip(res["simt"], res[name]):
+            assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("shape,eng_name", [((2, 1200, 384, 8), "tc"), ((2, 1200, 384, 8), "tc1"),
+                                            ((1, 700, 64, 10), "tc1"), ((1, 300, 32, 6), "simt")])
+def test_pruned_rescoring_equals_full_rescoring(shape, eng_name):
+    """osc_knn_rescore_checked skips candidates that the engine's error bound proves to lie below the
+    exact (k+1)-th score; tables, weights and the k/(k+1) gap must equal the unpruned pass."""
+    import ctypes as C
+
+    import torch
+
+    from oscillink_b200 import _cabi
+
+    B, N, D, k = shape
+    lib = _cabi.load()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7 * N + D)
+    Y = torch.randn((B, N, D), generator=gen, device=dev)
+    flags = {"simt": _cabi.KNN_SIMT, "tc": _cabi.KNN_TC, "tc1": _cabi.KNN_TC1}[eng_name]
+    eng, kc, eps = _cabi.knn_plan(N, N, D, k, flags)
+    assert eng == flags and kc >= k + 4
+    st = torch.cuda.current_stream().cuda_stream
+    Yn, hi, lo = torch.empty_like(Y), torch.empty_like(Y), torch.empty_like(Y)
+    _cabi.check(lib.osc_normalize_rows(Y.data_ptr(), B * N, D, Yn.data_ptr(), hi.data_ptr(),
+                                       lo.data_ptr() if eng == _cabi.KNN_TC else None, st))
+    ci = torch.empty((B, N, kc), dtype=torch.int32, device=dev)
+    cs = torch.empty((B, N, kc), dtype=torch.float32, device=dev)
+    _cabi.check(lib.osc_knn_candidates(Yn.data_ptr(), Yn.data_ptr(), hi.data_ptr(), lo.data_ptr(), hi.data_ptr(),
+                                       lo.data_ptr(), B, N, 0, N, D, kc, eng, ci.data_ptr(), cs.data_ptr(),
+                                       None, 0, st), "candidates")
+    assert bool((cs[..., :-1] >= cs[..., 1:]).all()), "candidate lists must be sorted descending"
+    out = {}
+    for mode in ("full", "pruned"):
+        ti = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+        ts = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+        gap = torch.empty((B, N), dtype=torch.float32, device=dev)
+        if mode == "full":
+            _cabi.check(lib.osc_knn_rescore(Yn.data_ptr(), Yn.data_ptr(), B, N, N, D, ci.data_ptr(), kc, k,
+                                            ti.data_ptr(), ts.data_ptr(), gap.data_ptr(), st), "rescore")
+        else:
+            nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+            need = C.c_size_t(0)
+            _cabi.check(lib.osc_knn_rescore_workspace(B, N, C.byref(need)))
+            ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.osc_knn_rescore_checked(Yn.data_ptr(), Yn.data_ptr(), B, N, 0, N, D, ci.data_ptr(),
+                                                    cs.data_ptr(), kc, k, eps, ti.data_ptr(), ts.data_ptr(),
+                                                    gap.data_ptr(), nflag.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    st), "rescore_checked")
+            out["flagged"] = int(nflag.item())
+        torch.cuda.synchronize()
+        out[mode] = (ti.cpu().numpy(), ts.cpu().numpy(), gap.cpu().numpy())
+    assert out["flagged"] == 0  # (an exhaustive row sees columns outside the list: not comparable)
+    for a, b in zip(out["full"], out["pruned"]):
         assert np.array_equal(a, b)
 
 
