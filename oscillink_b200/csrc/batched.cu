@@ -54,6 +54,7 @@ struct BatchedK {
   int64_t batch, n_work;
   int N, kq, D, G, CH, cpl;
   int do_settle, do_ustar, do_dh;
+  int use_ybuf;  // the kernel was given Np float4 of shared memory for the Y-slab prefetch buffer
   float lamG, lamC, lamQ, dt;
   double tol_settle, tol_ustar;
   int max_iters_settle, max_iters_ustar;
@@ -82,6 +83,15 @@ __device__ __forceinline__ float4 f4_mul(float4 a, float4 b) {
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only: the other half of the 32-byte sector
+// belongs to the neighbouring slab and is picked up from L2 by whoever runs that one)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ---- block reductions of per-column partials ---------------------------------------------------
 // All 32 lanes of a warp hold partials of the SAME 4 columns.  The butterfly halves the number of
@@ -154,38 +164,98 @@ __device__ __forceinline__ float4 bcast4(float q) {
                      __shfl_sync(0xffffffffu, q, 2), __shfl_sync(0xffffffffu, q, 3));
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2) ----------------------------------------
+// The kernel issues about as many instructions as its shared-memory pipe can take wavefronts, so the
+// float4 arithmetic runs on register PAIRS: fma.rn.f32x2 is two IEEE fp32 FMAs in one issue slot
+// (bit-identical to fmaf per lane), and a scalar weight enters as the {w, w} broadcast operand.
+typedef unsigned long long u64;
+struct V4 {
+  u64 lo, hi;  // {x, y}, {z, w}
+};
+__device__ __forceinline__ u64 pk2(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 upk2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ V4 v4_zero() { return V4{0ull, 0ull}; }
+__device__ __forceinline__ V4 to_v4(float4 f) { return V4{pk2(f.x, f.y), pk2(f.z, f.w)}; }
+__device__ __forceinline__ float4 to_f4(V4 v) {
+  const float2 a = upk2(v.lo), b = upk2(v.hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ V4 v4_bc(float s) {
+  const u64 t = pk2(s, s);
+  return V4{t, t};
+}
+__device__ __forceinline__ V4 v4_fma(V4 a, V4 b, V4 c) { return V4{fma2(a.lo, b.lo, c.lo), fma2(a.hi, b.hi, c.hi)}; }
+__device__ __forceinline__ V4 v4_fma_s(float s, V4 b, V4 c) {
+  const u64 t = pk2(s, s);
+  return V4{fma2(t, b.lo, c.lo), fma2(t, b.hi, c.hi)};
+}
+__device__ __forceinline__ V4 v4_mul(V4 a, V4 b) { return V4{mul2(a.lo, b.lo), mul2(a.hi, b.hi)}; }
+__device__ __forceinline__ V4 v4_mul_s(float s, V4 b) {
+  const u64 t = pk2(s, s);
+  return V4{mul2(t, b.lo), mul2(t, b.hi)};
+}
+__device__ __forceinline__ V4 v4_sub(V4 a, V4 b) { return V4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
+__device__ __forceinline__ V4 lds_v4(const void* p) {
+  const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
+  return V4{t.x, t.y};
+}
+__device__ __forceinline__ void sts_v4(void* p, V4 v) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v.lo, v.hi); }
+
 template <int TPT>
 struct Slab {
-  float4 X[TPT], R[TPT], AP[TPT];
+  V4 X[TPT], R[TPT], AP[TPT];
 };
 
 // sum_t W_t p[nbr_t] for one row; graph image is slot-major [c][row]
 template <int KQ>
-__device__ __forceinline__ float4 gather_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
-                                             int row, int N, int kq_rt) {
-  float4 acc = f4_zero();
+__device__ __forceinline__ V4 gather_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
+                                         int row, int N, int kq_rt) {
+  V4 acc = v4_zero();
   const int kq = KQ > 0 ? KQ : kq_rt;
   const char* pb = reinterpret_cast<const char*>(p_s);
 #pragma unroll
   for (int c = 0; c < kq; ++c) {
     const ushort4 jj = nbr_s[c * N + row];
     const float4 ww = w_s[c * N + row];
-    acc = f4_fma(ww.x, *reinterpret_cast<const float4*>(pb + jj.x), acc);
-    acc = f4_fma(ww.y, *reinterpret_cast<const float4*>(pb + jj.y), acc);
-    acc = f4_fma(ww.z, *reinterpret_cast<const float4*>(pb + jj.z), acc);
-    acc = f4_fma(ww.w, *reinterpret_cast<const float4*>(pb + jj.w), acc);
+    acc = v4_fma_s(ww.x, lds_v4(pb + jj.x), acc);
+    acc = v4_fma_s(ww.y, lds_v4(pb + jj.y), acc);
+    acc = v4_fma_s(ww.z, lds_v4(pb + jj.z), acc);
+    acc = v4_fma_s(ww.w, lds_v4(pb + jj.w), acc);
   }
   return acc;
 }
-__device__ __forceinline__ float4 combine_row(float4 own, float4 acc, float diag, float offc) {
-  return make_float4(diag * own.x - offc * acc.x, diag * own.y - offc * acc.y,
-                     diag * own.z - offc * acc.z, diag * own.w - offc * acc.w);
+// diag * own - offc * acc   (noffc = -offc)
+__device__ __forceinline__ V4 combine_row(V4 own, V4 acc, float diag, float noffc) {
+  return v4_fma_s(noffc, acc, v4_mul_s(diag, own));
 }
 // A(p) for one row: diag*p_own - offc * sum_t W_t p[nbr_t]
 template <int KQ>
-__device__ __forceinline__ float4 apply_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
-                                            int row, int N, int kq_rt, float diag, float offc) {
-  return combine_row(p_s[row], gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq_rt), diag, offc);
+__device__ __forceinline__ V4 apply_row(const float4* p_s, const ushort4* nbr_s, const float4* w_s,
+                                        int row, int N, int kq_rt, float diag, float noffc) {
+  return combine_row(lds_v4(p_s + row), gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq_rt), diag, noffc);
 }
 
 // One PCG solve for this CTA's slab (solver.py:15-37).  On exit st.X holds the iterate of the
@@ -208,46 +278,44 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   float4* redA = red;               // init r.z, then p.Ap
   float4* redB = red + RED_F4;      // r.r
   float4* redC = red + 2 * RED_F4;  // r.z'
+  const float noffc = -c.offc;
   // Rows tid + T*m >= N are PAD rows: zero state, zero weights, neighbour offset 0.  They run through
   // every phase unguarded (all their values stay 0 and add 0 to the reductions), which keeps the
   // per-row work free of per-thread branches so the compiler interleaves the TPT rows' load chains.
   if (acc_in == nullptr) {
 #pragma unroll
-    for (int m = 0; m < TPT; ++m) p_s[tid + T * m] = st.X[m];
+    for (int m = 0; m < TPT; ++m) sts_v4(p_s + tid + T * m, st.X[m]);
   }
   __syncthreads();  // x0 visible; diag_s, im_s of this solve visible
   // ---- r0 = b - A x0 ; z0 ; rz
-  float4 part = f4_zero();
+  V4 part = v4_zero();
 #pragma unroll
   for (int m = 0; m < TPT; ++m) {
     const int row = tid + T * m;
-    float4 g;
+    V4 g;
     if (acc_in != nullptr) {
-      g = act[m] ? acc_in[row] : f4_zero();
+      g = act[m] ? lds_v4(acc_in + row) : v4_zero();
     } else {
       g = gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq);
-      if (acc_out != nullptr && act[m]) acc_out[row] = g;
+      if (acc_out != nullptr && act[m]) sts_v4(acc_out + row, g);
     }
-    const float4 a = combine_row(st.X[m], g, GATES ? diag_s[row] : c.diag_u, c.offc);
-    float4 r = st.R[m];
-    r = make_float4(r.x - a.x, r.y - a.y, r.z - a.z, r.w - a.w);
+    const V4 a = combine_row(st.X[m], g, GATES ? diag_s[row] : c.diag_u, noffc);
+    const V4 r = v4_sub(st.R[m], a);
     st.R[m] = r;
     if (GATES) {
-      const float imr = im_s[row];
-      part = f4_add(part, f4_mul(r, make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr)));
+      part = v4_fma(r, v4_mul_s(im_s[row], r), part);
     } else {
-      part = f4_add(part, f4_mul(r, r));
+      part = v4_fma(r, r, part);
     }
   }
-  warp_reduce4(part, redA + warp, lane);
+  warp_reduce4(to_f4(part), redA + warp, lane);
   __syncthreads();  // also: every gather of x0 has completed
   float rz = block_total_c(redA, nw, lane);  // component lane&3
   if (!GATES) rz *= c.im_u;
 #pragma unroll
   for (int m = 0; m < TPT; ++m) {
     const float imr = GATES ? im_s[tid + T * m] : c.im_u;
-    const float4 r = st.R[m];
-    p_s[tid + T * m] = make_float4(r.x * imr, r.y * imr, r.z * imr, r.w * imr);  // p0 = z0
+    sts_v4(p_s + tid + T * m, v4_mul_s(imr, st.R[m]));  // p0 = z0
   }
   __syncthreads();
 
@@ -255,47 +323,41 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   float mx;
   while (true) {
     // ---- A: Ap, p.Ap
-    part = f4_zero();
+    part = v4_zero();
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
-      const float4 own = p_s[row];
+      const V4 own = lds_v4(p_s + row);
       st.AP[m] = combine_row(own, gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq),
-                             GATES ? diag_s[row] : c.diag_u, c.offc);
-      part = f4_add(part, f4_mul(own, st.AP[m]));
+                             GATES ? diag_s[row] : c.diag_u, noffc);
+      part = v4_fma(own, st.AP[m], part);
     }
-    warp_reduce4(part, redA + warp, lane);
+    warp_reduce4(to_f4(part), redA + warp, lane);
     __syncthreads();
     const float pap = block_total_c(redA, nw, lane);
     const float4 alpha = bcast4(__fdiv_rn(rz, pap + 1e-18f));
+    const V4 al = to_v4(alpha);
+    const V4 nal = to_v4(make_float4(-alpha.x, -alpha.y, -alpha.z, -alpha.w));
     // ---- C: x, r update; rr and rz'
-    float4 prr = f4_zero(), prz = f4_zero();
+    V4 prr = v4_zero(), prz = v4_zero();
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
-      const float4 p = p_s[row];
-      float4 x = st.X[m], r = st.R[m];
-      const float4 ap = st.AP[m];
-      x = make_float4(fmaf(p.x, alpha.x, x.x), fmaf(p.y, alpha.y, x.y), fmaf(p.z, alpha.z, x.z),
-                      fmaf(p.w, alpha.w, x.w));
-      r = make_float4(fmaf(-ap.x, alpha.x, r.x), fmaf(-ap.y, alpha.y, r.y), fmaf(-ap.z, alpha.z, r.z),
-                      fmaf(-ap.w, alpha.w, r.w));
-      st.X[m] = x;
+      const V4 p = lds_v4(p_s + row);
+      st.X[m] = v4_fma(p, al, st.X[m]);
+      const V4 r = v4_fma(st.AP[m], nal, st.R[m]);
       st.R[m] = r;
-      prr = f4_add(prr, f4_mul(r, r));
-      if (GATES) {
-        const float im = im_s[row];
-        prz = f4_add(prz, f4_mul(r, make_float4(r.x * im, r.y * im, r.z * im, r.w * im)));
-      }
+      prr = v4_fma(r, r, prr);
+      if (GATES) prz = v4_fma(r, v4_mul_s(im_s[row], r), prz);
     }
     float rr, rzn;
     if (GATES) {
-      warp_reduce8(prr, prz, redB + warp, redC + warp, lane);
+      warp_reduce8(to_f4(prr), to_f4(prz), redB + warp, redC + warp, lane);
       __syncthreads();
       rr = block_total_c(redB, nw, lane);
       rzn = block_total_c(redC, nw, lane);
     } else {
-      warp_reduce4(prr, redB + warp, lane);
+      warp_reduce4(to_f4(prr), redB + warp, lane);
       __syncthreads();
       rr = block_total_c(redB, nw, lane);
       rzn = rr * c.im_u;
@@ -307,16 +369,13 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
                                  : ((double)__fsqrt_rn(mx) <= tol || it >= max_iters);
     if (stop) break;
     // ---- E: p = z + beta p   (z = r / (Mdiag + 1e-12), recomputed from r: one FMUL per element)
-    const float4 beta = bcast4(__fdiv_rn(rzn, rz + 1e-18f));
+    const V4 beta = to_v4(bcast4(__fdiv_rn(rzn, rz + 1e-18f)));
     rz = rzn;
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
       const float im = GATES ? im_s[row] : c.im_u;
-      const float4 p = p_s[row];
-      const float4 r = st.R[m];
-      p_s[row] = make_float4(fmaf(p.x, beta.x, r.x * im), fmaf(p.y, beta.y, r.y * im),
-                             fmaf(p.z, beta.z, r.z * im), fmaf(p.w, beta.w, r.w * im));
+      sts_v4(p_s + row, v4_fma(lds_v4(p_s + row), beta, v4_mul_s(im, st.R[m])));
     }
     __syncthreads();
     ++it;
@@ -434,6 +493,11 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
   // with gates: [Np] operator diagonal and [Np] 1/(Mdiag + 1e-12) (not allocated otherwise)
   float* diag_s = reinterpret_cast<float*>(nbr_s + (size_t)Np * kq);
   float* im_s = diag_s + Np;
+  // Y-slab prefetch buffer [Np] float4 (P.use_ybuf): the 4 columns of Y this CTA works on next are
+  // copied with cp.async while the current slab is still iterating, so the set-up phases of a slab
+  // (settle RHS, U* RHS / x0, the u0 of the deltaH identity) read shared memory instead of waiting on
+  // HBM three times per slab.  Every thread copies and reads only ITS OWN rows: no barrier involved.
+  float4* ybuf = reinterpret_cast<float4*>(GATES ? im_s + Np : diag_s);
   // pad rows are written here once and never again (staging and set-up touch rows < N only)
   for (int e = tid; e < Np * kq; e += T) {
     w_s[e] = f4_zero();
@@ -459,6 +523,15 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
   float4* scr_t1 = scr_acc + N;
   const bool list_mode = P.fix_list != nullptr;
   const int64_t n_work = list_mode ? (int64_t)(*P.fix_count) : P.n_work;
+  const bool use_ybuf = P.use_ybuf != 0;
+  bool ybuf_ahead = false;  // ybuf already holds / is receiving the slab about to be processed
+  auto ybuf_fetch = [&](int64_t fb, int fs) {
+    const float* src = P.Y + fb * (int64_t)N * P.D + fs * SC;
+#pragma unroll
+    for (int m = 0; m < TPT; ++m)
+      if (act[m]) cp_async16(ybuf + tid + T * m, src + (int64_t)(tid + T * m) * P.D);
+    cp_async_commit();
+  };
   for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
     int64_t b;
     int s0, s1, Fs = 0, Fu = 0;
@@ -497,6 +570,25 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
       const float4 psi4 = *reinterpret_cast<const float4*>(P.psi + b * P.D + col);
       Slab<TPT> st;
       float rr = 0.f;
+      if (use_ybuf) {
+        if (!ybuf_ahead) ybuf_fetch(b, s);
+        cp_async_wait_all();
+        ybuf_ahead = false;
+      }
+      // issued once this slab has read Y for the last time: the next slab of this work item, or the
+      // first slab of this CTA's next work item
+      auto ybuf_next = [&]() {
+        if (!use_ybuf) return;
+        if (s + 1 < s1) {
+          ybuf_fetch(b, s + 1);
+          ybuf_ahead = true;
+        } else if (!list_mode && wk + gridDim.x < n_work) {
+          const int64_t wn = wk + gridDim.x;
+          const int64_t bn = wn / P.cpl;
+          ybuf_fetch(bn, (int)(wn - bn * P.cpl) * P.CH);
+          ybuf_ahead = true;
+        }
+      };
       // ---------------- settle: (I + dt M) U+ = U + dt (lamG Y + lamQ b psi^T), x0 = U
       if (P.do_settle) {
         SolveCoef c;
@@ -517,10 +609,10 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
-          st.X[m] = st.R[m] = st.AP[m] = f4_zero();
+          st.X[m] = st.R[m] = st.AP[m] = v4_zero();
           if (act[m]) {
             const int row = tid + T * m;
-            const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
+            const float4 y = use_ybuf ? ybuf[row] : *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
             const float4 u = P.U_in ? *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col) : y;
             const float bq = GATES ? gb[row] : 1.0f;
             const float4 rhs = make_float4(
@@ -528,18 +620,19 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
                 __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
                 __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.z))),
                 __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
-            st.X[m] = u;
-            st.R[m] = make_float4(__fadd_rn(u.x, __fmul_rn(P.dt, rhs.x)), __fadd_rn(u.y, __fmul_rn(P.dt, rhs.y)),
-                                  __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w)));
+            st.X[m] = to_v4(u);
+            st.R[m] = to_v4(make_float4(__fadd_rn(u.x, __fmul_rn(P.dt, rhs.x)), __fadd_rn(u.y, __fmul_rn(P.dt, rhs.y)),
+                                        __fadd_rn(u.z, __fmul_rn(P.dt, rhs.z)), __fadd_rn(u.w, __fmul_rn(P.dt, rhs.w))));
           }
         }
+        if (!P.do_ustar) ybuf_next();
         const int iters = slab_solve<TPT, KQ, T, GATES>(st, c, P.tol_settle, P.max_iters_settle, Fs, Np, kq,
                                                      p_s, diag_s, im_s, nbr_s, w_s, red, act, &rr,
                                                      share_r0 ? scr_acc : nullptr, nullptr);
         if (Uo != nullptr) {
 #pragma unroll
           for (int m = 0; m < TPT; ++m)
-            if (act[m]) *reinterpret_cast<float4*>(Uo + (int64_t)(tid + T * m) * P.D + col) = st.X[m];
+            if (act[m]) *reinterpret_cast<float4*>(Uo + (int64_t)(tid + T * m) * P.D + col) = to_f4(st.X[m]);
         }
         if (dh_fast) {
           // (I + dt M) U = b - r_s with b = U_in + dt RHS  =>  M U = RHS + (U_in - U - r_s)/dt
@@ -548,8 +641,10 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
               const int row = tid + T * m;
-              const float4 u0 = *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col);
-              const float4 x = st.X[m], r = st.R[m];
+              const float4 u0 = (use_ybuf && P.U_in == nullptr)
+                                    ? ybuf[row]
+                                    : *reinterpret_cast<const float4*>(Ub + (int64_t)row * P.D + col);
+              const float4 x = to_f4(st.X[m]), r = to_f4(st.R[m]);
               scr_t1[row] = make_float4(((u0.x - x.x) - r.x) * idt, ((u0.y - x.y) - r.y) * idt,
                                         ((u0.z - x.z) - r.z) * idt, ((u0.w - x.w) - r.w) * idt);
             }
@@ -577,19 +672,20 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
         }
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
-          st.X[m] = st.R[m] = st.AP[m] = f4_zero();
+          st.X[m] = st.R[m] = st.AP[m] = v4_zero();
           if (act[m]) {
             const int row = tid + T * m;
-            const float4 y = *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
+            const float4 y = use_ybuf ? ybuf[row] : *reinterpret_cast<const float4*>(Yb + (int64_t)row * P.D + col);
             const float bq = GATES ? gb[row] : 1.0f;
-            st.X[m] = y;
-            st.R[m] = make_float4(
+            st.X[m] = to_v4(y);
+            st.R[m] = to_v4(make_float4(
                 __fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.x))),
                 __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.y))),
                 __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.z))),
-                __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w))));
+                __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, __fmul_rn(bq, psi4.w)))));
           }
         }
+        ybuf_next();
         const int iters = slab_solve<TPT, KQ, T, GATES>(st, c, P.tol_ustar, P.max_iters_ustar, Fu, Np, kq,
                                                      p_s, diag_s, im_s, nbr_s, w_s, red, act, &rr, nullptr,
                                                      share_r0 ? scr_acc : nullptr);
@@ -597,7 +693,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           float* So = P.Ustar_out + b * (int64_t)N * P.D;
 #pragma unroll
           for (int m = 0; m < TPT; ++m)
-            if (act[m]) *reinterpret_cast<float4*>(So + (int64_t)(tid + T * m) * P.D + col) = st.X[m];
+            if (act[m]) *reinterpret_cast<float4*>(So + (int64_t)(tid + T * m) * P.D + col) = to_f4(st.X[m]);
         }
         if (tid == 0) P.rec[(b * 2 + 1) * P.G + s] = make_int2(iters, __float_as_int(rr));
         // ---------------- deltaH = <U - U*, M (U - U*)>
@@ -612,7 +708,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
               const int row = tid + T * m;
               const float4 u = *reinterpret_cast<const float4*>(Uo + (int64_t)row * P.D + col);
               const float4 t1 = scr_t1[row];
-              const float4 x = st.X[m], r = st.R[m];
+              const float4 x = to_f4(st.X[m]), r = to_f4(st.R[m]);
               const float4 d = make_float4(__fsub_rn(u.x, x.x), __fsub_rn(u.y, x.y), __fsub_rn(u.z, x.z),
                                            __fsub_rn(u.w, x.w));
               part = f4_add(part, f4_mul(d, f4_add(t1, r)));
@@ -633,7 +729,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
               // the settled state: written by this very thread a moment ago (U_out), or the caller's U
               const float* usrc = P.do_settle ? Uo : Ub;
               const float4 u = *reinterpret_cast<const float4*>(usrc + (int64_t)row * P.D + col);
-              const float4 x = st.X[m];
+              const float4 x = to_f4(st.X[m]);
               p_s[row] = make_float4(__fsub_rn(u.x, x.x), __fsub_rn(u.y, x.y), __fsub_rn(u.z, x.z),
                                      __fsub_rn(u.w, x.w));
             }
@@ -644,7 +740,7 @@ __global__ void __launch_bounds__(MAXT, MINB) batched_settle_kernel(BatchedK P) 
           for (int m = 0; m < TPT; ++m) {
             if (act[m]) {
               const int row = tid + T * m;
-              const float4 a = apply_row<KQ>(p_s, nbr_s, w_s, row, Np, kq, GATES ? diag_s[row] : c.diag_u, c.offc);
+              const float4 a = to_f4(apply_row<KQ>(p_s, nbr_s, w_s, row, Np, kq, GATES ? diag_s[row] : c.diag_u, -c.offc));
               part = f4_add(part, f4_mul(p_s[row], a));
             }
           }
@@ -734,6 +830,8 @@ static size_t batched_smem(int64_t N, int k, bool gates) {
 
 // static shared memory of the kernel variant that serves N (p_static[MAXT * TPT])
 static size_t batched_static_smem(int64_t N) { return (size_t)maxt_for(N) * tpt_for(N) * 16; }
+// the optional Y-slab prefetch buffer (dynamic, behind the gates arrays)
+static size_t batched_ybuf_smem(int64_t N) { return (size_t)maxt_for(N) * tpt_for(N) * 16; }
 
 int batched_supported(int64_t N, int D, int k) {
   if (N < 1 || N > 2560) return 0;
@@ -812,7 +910,7 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   P.pk_nbr = pn; P.pk_w = pw;
   P.scratch = scratch;
   P.batch = g->batch; P.N = N; P.kq = kq; P.D = a->D; P.G = G;
-  P.CH = 2;
+  P.CH = 4;  // slabs per staged graph image (measured on B200 at B=1440: CH=2 23.07 ms, 4 22.65, 8 23.55)
   {
     const char* e = getenv("OSC_BATCHED_CHUNK");  // dev-only: slabs per staged graph image
     if (e && atoi(e) >= 1) P.CH = atoi(e);
@@ -837,14 +935,27 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   else if (tpt == 2) fn = pick_kq<2, 320, 2>(kq, gates);
   else if (tpt == 3) fn = pick_kq<3, 320, 2>(kq, gates);
   else fn = pick_kq<4, 320, 2>(kq, gates);
-  OSC_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, threads, smem));
+  {
+    // the prefetch buffer is taken only if it costs no resident CTA
+    const size_t smem_y = smem + batched_ybuf_smem(N);
+    const bool fits = smem_y + batched_static_smem(N) <= 227 * 1024;
+    const char* e = getenv("OSC_BATCHED_YBUF");  // dev-only A/B switch
+    const bool want = !(e && atoi(e) == 0);
+    OSC_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(fits ? smem_y : smem)));
+    OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, threads, smem));
+    int occ_y = 0;
+    if (fits && want)
+      OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_y, (const void*)fn, threads, smem_y));
+    P.use_ybuf = (occ_y >= 1 && occ_y >= (occ < SCR_CTAS_PER_SM ? occ : SCR_CTAS_PER_SM)) ? 1 : 0;
+  }
+  const size_t smem_launch = P.use_ybuf ? smem + batched_ybuf_smem(N) : smem;
   if (occ < 1) return fail(OSC_ERR_UNSUPPORTED, "batched_settle: kernel does not fit on an SM");
   if (occ > SCR_CTAS_PER_SM) occ = SCR_CTAS_PER_SM;
   const int64_t resident = (int64_t)occ * sm_count();
   const unsigned grid = (unsigned)(P.n_work < resident ? P.n_work : resident);
-  fn<<<grid, threads, smem, st>>>(P);
+  fn<<<grid, threads, smem_launch, st>>>(P);
   OSC_LAUNCH_CHECK("batched_settle_kernel");
 
   batched_resolve_kernel<<<(unsigned)((g->batch + 127) / 128), 128, 0, st>>>(
@@ -856,7 +967,7 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
     Q.fix_count = fix_count;
     const int64_t worst = g->batch * G;
     const unsigned grid2 = (unsigned)(worst < resident ? worst : resident);
-    fn<<<grid2, threads, smem, st>>>(Q);
+    fn<<<grid2, threads, smem_launch, st>>>(Q);
     OSC_LAUNCH_CHECK("batched_settle_kernel(fix)");
   }
   int force_bad = 0;
