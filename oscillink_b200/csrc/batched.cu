@@ -312,10 +312,15 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
   __syncthreads();  // also: every gather of x0 has completed
   float rz = block_total_c(redA, nw, lane);  // component lane&3
   if (!GATES) rz *= c.im_u;
+  // The thread's own rows of p stay in registers from the p update to the next gather phase: they sit
+  // in the AP slots, which are dead between the r update and the next A(p).  With the x update moved
+  // next to the p update (where p is read anyway) the own-row traffic on the shared-memory pipe is one
+  // load + one store per row and iteration instead of three loads + one store.
 #pragma unroll
   for (int m = 0; m < TPT; ++m) {
     const float imr = GATES ? im_s[tid + T * m] : c.im_u;
-    sts_v4(p_s + tid + T * m, v4_mul_s(imr, st.R[m]));  // p0 = z0
+    st.AP[m] = v4_mul_s(imr, st.R[m]);  // p0 = z0
+    sts_v4(p_s + tid + T * m, st.AP[m]);
   }
   __syncthreads();
 
@@ -327,7 +332,7 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
-      const V4 own = lds_v4(p_s + row);
+      const V4 own = st.AP[m];
       st.AP[m] = combine_row(own, gather_row<KQ>(p_s, nbr_s, w_s, row, N, kq),
                              GATES ? diag_s[row] : c.diag_u, noffc);
       part = v4_fma(own, st.AP[m], part);
@@ -338,17 +343,14 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     const float4 alpha = bcast4(__fdiv_rn(rz, pap + 1e-18f));
     const V4 al = to_v4(alpha);
     const V4 nal = to_v4(make_float4(-alpha.x, -alpha.y, -alpha.z, -alpha.w));
-    // ---- C: x, r update; rr and rz'
+    // ---- C: r update; rr and rz'   (x += alpha p is applied in E / at the stop, same arithmetic)
     V4 prr = v4_zero(), prz = v4_zero();
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
-      const int row = tid + T * m;
-      const V4 p = lds_v4(p_s + row);
-      st.X[m] = v4_fma(p, al, st.X[m]);
       const V4 r = v4_fma(st.AP[m], nal, st.R[m]);
       st.R[m] = r;
       prr = v4_fma(r, r, prr);
-      if (GATES) prz = v4_fma(r, v4_mul_s(im_s[row], r), prz);
+      if (GATES) prz = v4_fma(r, v4_mul_s(im_s[tid + T * m], r), prz);
     }
     float rr, rzn;
     if (GATES) {
@@ -367,15 +369,22 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
     // identical in every thread (same summation order) -> uniform branch
     const bool stop = forced > 0 ? (it >= forced)
                                  : ((double)__fsqrt_rn(mx) <= tol || it >= max_iters);
-    if (stop) break;
-    // ---- E: p = z + beta p   (z = r / (Mdiag + 1e-12), recomputed from r: one FMUL per element)
+    if (stop) {
+#pragma unroll
+      for (int m = 0; m < TPT; ++m) st.X[m] = v4_fma(lds_v4(p_s + tid + T * m), al, st.X[m]);
+      break;
+    }
+    // ---- E: x += alpha p ; p = z + beta p   (z = r / (Mdiag + 1e-12), recomputed from r)
     const V4 beta = to_v4(bcast4(__fdiv_rn(rzn, rz + 1e-18f)));
     rz = rzn;
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       const int row = tid + T * m;
       const float im = GATES ? im_s[row] : c.im_u;
-      sts_v4(p_s + row, v4_fma(lds_v4(p_s + row), beta, v4_mul_s(im, st.R[m])));
+      const V4 p = lds_v4(p_s + row);
+      st.X[m] = v4_fma(p, al, st.X[m]);
+      st.AP[m] = v4_fma(p, beta, v4_mul_s(im, st.R[m]));
+      sts_v4(p_s + row, st.AP[m]);
     }
     __syncthreads();
     ++it;
