@@ -7,6 +7,8 @@
 //
 // The tensor-core engine (knn_tc.cu) produces the same candidate lists; both feed
 // knn_rescore_kernel, which is what fixes the final neighbour sets.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace osc {
@@ -146,8 +148,30 @@ knn_simt_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, in
 }
 
 // ---------------------------------------------------------------- canonical re-scoring
+// Totals of four per-lane fp64 partials at once: a butterfly that halves the number of live values per
+// step (8 + 4 + 3*2 = 18 SHFL and 6 DADD instead of 4 x (10 + 5)).  Lane 8*i ends up with the total
+// of a[i].  Every pair sum is the one warp_sum() forms (x_l + x_{l^off}, IEEE addition commutes), so
+// the totals are bit-identical to four warp_sum() calls -- knn_exact_rows_kernel relies on that.
+__device__ __forceinline__ double warp_sum4(const double (&a)[4], int lane) {
+  const bool b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1;
+  double k0 = b4 ? a[2] : a[0], k1 = b4 ? a[3] : a[1];
+  const double s0 = b4 ? a[0] : a[2], s1 = b4 ? a[1] : a[3];
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  double k = b3 ? k1 : k0;
+  const double s = b3 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;  // lane: total of a[(b4 << 1) | b3]
+}
+
 // One warp per query row.  dynamic smem: warps * kc * (float + int).
-__global__ void __launch_bounds__(256)
+// QC > 0: D <= 128 * QC and D % 4 == 0 -- the query row is converted to fp64 once and kept in
+// registers (the pass is issue-bound: conversions and shuffles, not L2 bandwidth).  QC == 0: any D.
+template <int QC>
+__global__ void __launch_bounds__(256, QC == 0 ? 4 : 2)
 knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, int64_t n_rows,
                    int64_t N, int D, const int32_t* __restrict__ cand_idx, int kc, int k,
                    int32_t* __restrict__ top_idx, float* __restrict__ top_sim,
@@ -172,69 +196,120 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
   int n_keep = kc;
   if (cs != nullptr && kc > k) {
     const float thr = cs[k] - 2.0f * eps;
-    int cnt = 0;
-    for (int c = lane; c < kc; c += 32) cnt += (cs[c] >= thr) ? 1 : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, lane < kc && cs[lane < kc ? lane : 0] >= thr);
+    int cnt = __popc(m);
+    for (int c = 32 + lane; c < kc; c += 32) cnt += (cs[c] >= thr) ? 1 : 0;  // kc > 32 only
+    if (kc > 32) {
+      int extra = cnt - __popc(m);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      for (int off = 16; off > 0; off >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, off);
+      cnt = __popc(m) + extra;
+    }
     n_keep = cnt < k + 1 ? k + 1 : cnt;  // a prefix of the sorted list; -inf tails carry idx -1
     if (n_keep > kc) n_keep = kc;
   }
-  for (int c = n_keep + lane; c < kc; c += 32) sj[c] = -1;
   // Four candidates at a time: their row fetches are independent, so a lane keeps up to 4 x D/128
-  // 16-byte loads in flight (the pass is bound by L2/HBM latency, not by the fp64 FMAs).  Lane l
-  // owns elements {4l..4l+3} + 128 t of every row, for (i,j) and (j,i) alike: S stays symmetric.
+  // 16-byte loads in flight.  Lane l owns elements {4l..4l+3} + 128 t of every row, for (i,j) and
+  // (j,i) alike: S stays symmetric.  Slots past n_keep re-read the query row (always valid memory,
+  // L1 hit) so no load is predicated; their totals are discarded.
   const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(yi) | reinterpret_cast<uintptr_t>(all)) % 16 == 0);
-  for (int c0 = 0; c0 < n_keep; c0 += 4) {
-    int jc[4];
-    const float* yj[4];
-    double acc[4];
+  if (QC > 0 && v4) {
+    constexpr int QN = QC > 0 ? QC : 1;
+    double q[QN][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      jc[u] = (c0 + u < n_keep) ? ci[c0 + u] : -1;
-      yj[u] = all + (int64_t)(jc[u] >= 0 ? jc[u] : 0) * D;
-      acc[u] = 0.0;
+    for (int t = 0; t < QC; ++t) {
+      const int d = lane * 4 + 128 * t;
+      const float4 f = d < D ? *reinterpret_cast<const float4*>(yi + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q[t][0] = (double)f.x; q[t][1] = (double)f.y; q[t][2] = (double)f.z; q[t][3] = (double)f.w;
     }
-    if (v4) {
-      for (int d = lane * 4; d < D; d += 128) {
-        const float4 q = *reinterpret_cast<const float4*>(yi + d);
-        float4 x[4];
+    for (int c0 = 0; c0 < n_keep; c0 += 4) {
+      int jc[4];
+      const float* yj[4];
+      double acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        jc[u] = (c0 + u < n_keep) ? ci[c0 + u] : -1;
+        yj[u] = jc[u] >= 0 ? all + (int64_t)jc[u] * D : yi;
+        acc[u] = 0.0;
+      }
+      float4 x[QN][4];
+#pragma unroll
+      for (int t = 0; t < QC; ++t) {
+        const int d = lane * 4 + 128 * t;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          x[u] = jc[u] >= 0 ? *reinterpret_cast<const float4*>(yj[u] + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[t][u] = d < D ? *reinterpret_cast<const float4*>(yj[u] + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          acc[u] = fma((double)q.x, (double)x[u].x, acc[u]);
-          acc[u] = fma((double)q.y, (double)x[u].y, acc[u]);
-          acc[u] = fma((double)q.z, (double)x[u].z, acc[u]);
-          acc[u] = fma((double)q.w, (double)x[u].w, acc[u]);
+      for (int t = 0; t < QC; ++t) {
+        if (lane * 4 + 128 * t < D) {  // same FMA sequence per lane as the generic path
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[u] = fma(q[t][0], (double)x[t][u].x, acc[u]);
+            acc[u] = fma(q[t][1], (double)x[t][u].y, acc[u]);
+            acc[u] = fma(q[t][2], (double)x[t][u].z, acc[u]);
+            acc[u] = fma(q[t][3], (double)x[t][u].w, acc[u]);
+          }
         }
       }
-    } else {
-      for (int d = lane; d < D; d += 32) {
-        const double q = (double)yi[d];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (jc[u] >= 0) acc[u] = fma(q, (double)yj[u][d], acc[u]);
+      const double tot = warp_sum4(acc, lane);
+      const int u = lane >> 3;
+      const int ju = u == 0 ? jc[0] : (u == 1 ? jc[1] : (u == 2 ? jc[2] : jc[3]));
+      if ((lane & 7) == 0 && c0 + u < n_keep) {
+        sv[c0 + u] = ju >= 0 ? (float)tot : -INFINITY;
+        sj[c0 + u] = ju;
       }
     }
+  } else {
+    for (int c0 = 0; c0 < n_keep; c0 += 4) {
+      int jc[4];
+      const float* yj[4];
+      double acc[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double t = warp_sum(acc[u]);
-      if (lane == 0 && c0 + u < n_keep) {
-        sv[c0 + u] = jc[u] >= 0 ? (float)t : -INFINITY;
-        sj[c0 + u] = jc[u];
+      for (int u = 0; u < 4; ++u) {
+        jc[u] = (c0 + u < n_keep) ? ci[c0 + u] : -1;
+        yj[u] = jc[u] >= 0 ? all + (int64_t)jc[u] * D : yi;
+        acc[u] = 0.0;
+      }
+      if (v4) {
+        for (int d = lane * 4; d < D; d += 128) {
+          const float4 q = *reinterpret_cast<const float4*>(yi + d);
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(yj[u] + d);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[u] = fma((double)q.x, (double)x[u].x, acc[u]);
+            acc[u] = fma((double)q.y, (double)x[u].y, acc[u]);
+            acc[u] = fma((double)q.z, (double)x[u].z, acc[u]);
+            acc[u] = fma((double)q.w, (double)x[u].w, acc[u]);
+          }
+        }
+      } else {
+        for (int d = lane; d < D; d += 32) {
+          const double q = (double)yi[d];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(q, (double)yj[u][d], acc[u]);
+        }
+      }
+      const double tot = warp_sum4(acc, lane);
+      const int u = lane >> 3;
+      const int ju = u == 0 ? jc[0] : (u == 1 ? jc[1] : (u == 2 ? jc[2] : jc[3]));
+      if ((lane & 7) == 0 && c0 + u < n_keep) {
+        sv[c0 + u] = ju >= 0 ? (float)tot : -INFINITY;
+        sj[c0 + u] = ju;
       }
     }
   }
   __syncwarp();
   const int64_t o = (b * n_rows + r) * k;
   float kth = INFINITY, nxt = -INFINITY;
-  for (int c = lane; c < kc; c += 32) {
+  for (int c = lane; c < n_keep; c += 32) {
     const float s = sv[c];
     const int j = sj[c];
     if (j < 0) continue;
     int rank = 0;
-    for (int c2 = 0; c2 < kc; ++c2) {
+    for (int c2 = 0; c2 < n_keep; ++c2) {
       const int j2 = sj[c2];
       if (j2 >= 0 && c2 != c && better(sv[c2], j2, s, j)) ++rank;
     }
@@ -396,9 +471,19 @@ int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_
   dim3 grid((unsigned)((n_rows + warps - 1) / warps), (unsigned)batch);
   const bool check = cand_sim != nullptr && flagged != nullptr && n_flagged != nullptr;
   if (check) OSC_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(int), st));
-  knn_rescore_kernel<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k, top_idx,
-                                                     top_sim, gap, check ? cand_sim : nullptr, eps,
-                                                     check ? flagged : nullptr, n_flagged);
+  // Measured on B200 (4096 lattices N=1200 D=384, kc=16): the 64-register generic variant with 32
+  // resident warps per SM takes 10.6 ms, the variant that keeps the fp64 query row in registers
+  // (128 registers, 16 warps) 16.0 ms -- latency hiding wins over the saved conversions.
+  auto fn = knn_rescore_kernel<0>;
+  {
+    const char* e = getenv("OSC_RESCORE_HOIST");  // dev-only A/B switch
+    if (e && atoi(e) != 0)
+      fn = D <= 128 ? knn_rescore_kernel<1>
+           : D <= 256 ? knn_rescore_kernel<2>
+           : D <= 384 ? knn_rescore_kernel<3> : knn_rescore_kernel<0>;
+  }
+  fn<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k, top_idx, top_sim, gap,
+                                     check ? cand_sim : nullptr, eps, check ? flagged : nullptr, n_flagged);
   OSC_LAUNCH_CHECK("knn_rescore_kernel");
   if (check && (int64_t)kc < N - 1) {
     const size_t sm2 = (size_t)warps * (k + 1) * (sizeof(float) + sizeof(int)) + warps * sizeof(int);
