@@ -40,12 +40,15 @@ extern "C" {
 
 #define OSC_ABI_VERSION 1
 
-/* kNN engine selector for osc_knn_candidates (flags bits 0-1) */
+/* kNN engine selector for osc_knn_candidates (flags bits 0-2) */
 #define OSC_KNN_AUTO 0
 #define OSC_KNN_SIMT 1 /* fp32 CUDA-core tile kernel (any shape) */
 #define OSC_KNN_TC 2   /* tcgen05 3xTF32 tensor-core kernel (sm_100a) */
 #define OSC_KNN_TC1 3  /* tcgen05 single-product TF32 kernel: a third of the tensor work, scores only \
                           pre-select candidates (error bound OSC_KNN_EPS_TC1, wider candidate lists) */
+#define OSC_KNN_TCH 4  /* tcgen05 single-product fp16 kernel: same 11-bit operands and error bound as TC1, \
+                          half the operand bytes and twice the MMA rate; needs D % 8 == 0.  The q_hi /  \
+                          all_hi arguments then point at fp16 arrays (osc_normalize_rows_f16) */
 
 /* solve modes for osc_pcg_* / osc_batched_* */
 #define OSC_MODE_SETTLE 0     /* (I + dt M) X = U + dt RHS   lattice.py:170-192 */
@@ -100,6 +103,9 @@ int osc_device_info(int device, int* h_sm_count, int* h_smem_optin, int* h_cc);
  * OSC_KNN_TC1 reads hi only (pass Yn_lo = NULL). */
 int osc_normalize_rows(const float* Y, int64_t rows, int32_t D, float* Yn, float* Yn_hi,
                        float* Yn_lo, void* stream);
+/* Same normalisation; Yn_h16 ([rows][D] IEEE fp16, round-to-nearest of Yn) feeds OSC_KNN_TCH. */
+int osc_normalize_rows_f16(const float* Y, int64_t rows, int32_t D, float* Yn, void* Yn_h16,
+                           void* stream);
 
 /* Candidate pass.  For each of the `n_rows` query rows (global ids row0..row0+n_rows-1 of
  * every lattice in the batch) keep the kc best columns of Yn_q . Yn_all^T by (approximate

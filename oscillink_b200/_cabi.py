@@ -16,7 +16,8 @@ _lock = threading.Lock()
 _lib = None
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC1 = 0, 1, 2, 3
+KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC1, KNN_TCH = 0, 1, 2, 3, 4
+ENGINE_NAMES = {KNN_SIMT: "simt", KNN_TC: "tc", KNN_TC1: "tc1", KNN_TCH: "tch"}
 MODE_SETTLE, MODE_STATIONARY = 0, 1
 KNN_EPS = 1e-5  # OSC_KNN_EPS
 KNN_EPS_TC1 = 1e-3  # OSC_KNN_EPS_TC1
@@ -58,6 +59,7 @@ PROTOTYPES = {
     "osc_last_error": (C.c_char_p, []),
     "osc_device_info": (C.c_int, [C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]),
     "osc_normalize_rows": (C.c_int, [c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osc_normalize_rows_f16": (C.c_int, [c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p]),
     "osc_knn_candidates": (C.c_int, [c_void_p] * 6 + [c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32,
                                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "osc_knn_tc_supported": (C.c_int, [c_i64, c_i32, c_i32]),

@@ -92,7 +92,7 @@ class BatchedLattices:
         rows = B * N
         eng, kc, eps = _cabi.knn_plan(N, N, D, k, self._engine)
         use_tc = eng in (_cabi.KNN_TC, _cabi.KNN_TC1)
-        self.engine_used = {_cabi.KNN_SIMT: "simt", _cabi.KNN_TC: "tc", _cabi.KNN_TC1: "tc1"}[eng]
+        self.engine_used = _cabi.ENGINE_NAMES[eng]
         self.kc = kc
         Yn = torch.empty_like(self.Y)
         hi = torch.empty_like(self.Y) if use_tc else None
@@ -112,8 +112,13 @@ class BatchedLattices:
             self.events[name] = (e0, e1)
 
         P = _cabi.ptr
-        phase("normalize", lambda: lib.osc_normalize_rows(self.Y.data_ptr(), rows, D, Yn.data_ptr(),
-                                                          P(hi), P(lo), st))
+        if eng == _cabi.KNN_TCH:  # fp16 rows ride in the q_hi / all_hi arguments
+            hi = torch.empty(self.Y.shape, dtype=torch.float16, device=dev)
+            phase("normalize", lambda: lib.osc_normalize_rows_f16(self.Y.data_ptr(), rows, D, Yn.data_ptr(),
+                                                                  hi.data_ptr(), st))
+        else:
+            phase("normalize", lambda: lib.osc_normalize_rows(self.Y.data_ptr(), rows, D, Yn.data_ptr(),
+                                                              P(hi), P(lo), st))
         phase("knn_candidates", lambda: lib.osc_knn_candidates(
             Yn.data_ptr(), Yn.data_ptr(), P(hi), P(lo), P(hi), P(lo), B, N, 0, N, D, kc,
             eng, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st))

@@ -35,14 +35,15 @@ int sm_count() {
 }
 
 // launchers implemented in the kernel translation units
-int launch_normalize(const float*, int64_t, int, float*, float*, float*, cudaStream_t);
+int launch_normalize(const float*, int64_t, int, float*, float*, float*, cudaStream_t, void* h16 = nullptr);
 int launch_knn_simt(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, int, int32_t*,
                     float*, cudaStream_t);
 int knn_tc_supported(int64_t N, int D, int kc);
 int knn_tc1_supported(int64_t n_rows, int64_t N, int D, int kc);
+int knn_tch_supported(int64_t n_rows, int64_t N, int D, int kc);
 int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
                   int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
-                  int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st);
+                  int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st, bool f16 = false);
 int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, const int32_t*,
                    const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t);
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
@@ -92,7 +93,7 @@ int batched_settle(const osc_graph_t*, const osc_params_t*, const osc_batched_ar
 //  template width is used (k <= 8: 16, k <= 12: 24, else 32).
 static int candidate_width(int64_t N, int k, int eng) {
   int64_t kc = (int64_t)k + 4;
-  if (eng == OSC_KNN_TC1) {
+  if (eng == OSC_KNN_TC1 || eng == OSC_KNN_TCH) {
     const int want = 2 * k < 16 ? 16 : 2 * k;
     const int64_t wide = want <= 16 ? 16 : (want <= 24 ? 24 : 32);
     if (wide > kc) kc = wide;
@@ -102,27 +103,42 @@ static int candidate_width(int64_t N, int k, int eng) {
   return (int)kc;
 }
 
-static float engine_eps(int eng) { return eng == OSC_KNN_TC1 ? OSC_KNN_EPS_TC1 : OSC_KNN_EPS; }
+static float engine_eps(int eng) {
+  return (eng == OSC_KNN_TC1 || eng == OSC_KNN_TCH) ? OSC_KNN_EPS_TC1 : OSC_KNN_EPS;
+}
 
-// AUTO resolves to the single-product engine wherever it covers the shape: measured on B200 it builds
-// the same graphs (0 rows need the exhaustive path on Gaussian anchors) 1.33x faster at N=1200 D=384
-// and 3.4x faster at N=1M D=768 (7.36 s -> 2.19 s).  OSC_KNN_AUTO=tc forces the 3xTF32 engine (A/B).
-static bool auto_prefers_tc1() {
+// AUTO resolves to a single-product engine wherever one covers the shape -- fp16 operands first, tf32
+// where D % 8 != 0: measured on B200 they build the same graphs as the 3xTF32 engine (0 rows need the
+// exhaustive path on Gaussian anchors), tf32 1.33x faster at N=1200 D=384 and 3.4x faster at N=1M
+// D=768 (7.36 s -> 2.19 s).  OSC_KNN_AUTO=tc / tc1 / tch forces one engine (A/B switch).
+static int auto_choice() {
   const char* e = getenv("OSC_KNN_AUTO");
-  return !(e != nullptr && (strcmp(e, "tc") == 0 || strcmp(e, "TC") == 0));
+  if (e == nullptr) return OSC_KNN_AUTO;
+  if (strcmp(e, "tc") == 0 || strcmp(e, "TC") == 0) return OSC_KNN_TC;
+  if (strcmp(e, "tc1") == 0 || strcmp(e, "TC1") == 0) return OSC_KNN_TC1;
+  if (strcmp(e, "tch") == 0 || strcmp(e, "TCH") == 0) return OSC_KNN_TCH;
+  return OSC_KNN_AUTO;
 }
 
 // engine for `n_rows` query rows against N columns; -1: the requested engine does not cover the shape
 static int pick_engine(int flags, int64_t n_rows, int64_t N, int D, int k) {
-  const int want = flags & 3;
+  const int want = flags & 7;
   if (want == OSC_KNN_SIMT) return OSC_KNN_SIMT;
   const int ok3 = knn_tc_supported(N, D, candidate_width(N, k, OSC_KNN_TC));
   const int ok1 = knn_tc1_supported(n_rows, N, D, candidate_width(N, k, OSC_KNN_TC1));
+  const int okh = knn_tch_supported(n_rows, N, D, candidate_width(N, k, OSC_KNN_TCH));
   if (want == OSC_KNN_TC) return ok3 ? OSC_KNN_TC : -1;
   if (want == OSC_KNN_TC1) return ok1 ? OSC_KNN_TC1 : -1;
+  if (want == OSC_KNN_TCH) return okh ? OSC_KNN_TCH : -1;
   // AUTO: 128x256 tensor tiles only pay off once a lattice fills a few of them
   if (N < 256) return OSC_KNN_SIMT;
-  if (ok1 && k <= 16 && auto_prefers_tc1()) return OSC_KNN_TC1;
+  const int pref = auto_choice();
+  if (pref == OSC_KNN_TC && ok3) return OSC_KNN_TC;
+  if (pref == OSC_KNN_TC1 && ok1) return OSC_KNN_TC1;
+  if (k <= 16) {
+    if (okh && pref != OSC_KNN_TC1) return OSC_KNN_TCH;
+    if (ok1) return OSC_KNN_TC1;
+  }
   return ok3 ? OSC_KNN_TC : OSC_KNN_SIMT;
 }
 
@@ -154,6 +170,12 @@ int osc_normalize_rows(const float* Y, int64_t rows, int32_t D, float* Yn, float
   return launch_normalize(Y, rows, D, Yn, Yn_hi, Yn_lo, (cudaStream_t)stream);
 }
 
+int osc_normalize_rows_f16(const float* Y, int64_t rows, int32_t D, float* Yn, void* Yn_h16, void* stream) {
+  OSC_REQUIRE(Y != nullptr && Yn != nullptr && Yn_h16 != nullptr && rows >= 0 && D >= 1,
+              "normalize_rows_f16: bad argument");
+  return launch_normalize(Y, rows, D, Yn, nullptr, nullptr, (cudaStream_t)stream, Yn_h16);
+}
+
 int osc_knn_tc_supported(int64_t N, int32_t D, int32_t kc) { return knn_tc_supported(N, D, kc); }
 
 int osc_knn_plan(int64_t n_rows, int64_t N, int32_t D, int32_t k, int32_t flags, int32_t* h_engine,
@@ -183,11 +205,17 @@ int osc_knn_candidates(const float* Yn_q, const float* Yn_all, const float* q_hi
   if (batch == 0 || n_rows == 0) return OSC_OK;
   // The caller fixed kc (and the eps it will hand to the checked re-scoring), so AUTO never picks
   // the single-product engine here: that one is entered on explicit request only (osc_knn_plan).
-  int eng = flags & 3;
+  int eng = flags & 7;
   if (eng == OSC_KNN_AUTO) eng = (N >= 256 && knn_tc_supported(N, D, kc)) ? OSC_KNN_TC : OSC_KNN_SIMT;
   if ((eng == OSC_KNN_TC && !knn_tc_supported(N, D, kc)) ||
-      (eng == OSC_KNN_TC1 && !knn_tc1_supported(n_rows, N, D, kc)))
+      (eng == OSC_KNN_TC1 && !knn_tc1_supported(n_rows, N, D, kc)) ||
+      (eng == OSC_KNN_TCH && !knn_tch_supported(n_rows, N, D, kc)))
     return fail(OSC_ERR_UNSUPPORTED, "knn_candidates: tensor-core engine does not cover this shape");
+  if (eng == OSC_KNN_TCH) {
+    OSC_REQUIRE(q_hi && all_hi, "knn_candidates: TCH engine needs the fp16 rows (q_hi / all_hi)");
+    return launch_knn_tc(q_hi, nullptr, all_hi, nullptr, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
+                         true, (cudaStream_t)stream, true);
+  }
   if (eng == OSC_KNN_TC1) {
     OSC_REQUIRE(q_hi && all_hi, "knn_candidates: TC1 engine needs the tf32-rounded rows (hi)");
     return launch_knn_tc(q_hi, nullptr, all_hi, nullptr, batch, n_rows, row0, N, D, kc, cand_idx, cand_sim,
@@ -265,6 +293,7 @@ int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int3
   size_t b = align_up(rows * D * sizeof(float));                       // Yn
   if (eng == OSC_KNN_TC) b += 2 * align_up(rows * D * sizeof(float));  // hi, lo
   if (eng == OSC_KNN_TC1) b += align_up(rows * D * sizeof(float));     // hi
+  if (eng == OSC_KNN_TCH) b += align_up(rows * D * 2);                 // fp16 rows
   b += align_up(rows * kc * sizeof(int32_t)) + align_up(rows * kc * sizeof(float));  // candidates
   b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
   b += align_up(rows * sizeof(float));                                               // cap scale
@@ -308,6 +337,11 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   float *hi = nullptr, *lo = nullptr;
   if (eng == OSC_KNN_TC || eng == OSC_KNN_TC1) hi = ar.take<float>(rows * D);
   if (eng == OSC_KNN_TC) lo = ar.take<float>(rows * D);
+  uint16_t* h16 = nullptr;
+  if (eng == OSC_KNN_TCH) {
+    h16 = ar.take<uint16_t>(rows * D);
+    hi = reinterpret_cast<float*>(h16);  // handed to osc_knn_candidates as q_hi / all_hi
+  }
   int32_t* cand_idx = ar.take<int32_t>(rows * kc);
   float* cand_sim = ar.take<float>(rows * kc);
   int32_t* top_idx = ar.take<int32_t>(rows * k);
@@ -316,7 +350,7 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   int64_t* flagged = ar.take<int64_t>(rows);
   int* n_flagged = ar.take<int>(1);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
-  if ((rc = launch_normalize(Y, (int64_t)rows, D, Yn, hi, lo, st))) return rc;
+  if ((rc = launch_normalize(Y, (int64_t)rows, D, Yn, h16 ? nullptr : hi, lo, st, h16))) return rc;
   if ((rc = osc_knn_candidates(Yn, Yn, hi, lo, hi, lo, batch, N, 0, N, D, kc, eng, cand_idx, cand_sim,
                                nullptr, 0, stream)))
     return rc;

@@ -7,6 +7,8 @@
 //
 // The tensor-core engine (knn_tc.cu) produces the same candidate lists; both feed
 // knn_rescore_kernel, which is what fixes the final neighbour sets.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -23,7 +25,8 @@ __device__ __forceinline__ float to_tf32(float v) {
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ Y, int64_t rows,
                                                              int D, float* __restrict__ Yn,
                                                              float* __restrict__ hi,
-                                                             float* __restrict__ lo) {
+                                                             float* __restrict__ lo,
+                                                             __half* __restrict__ h16) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -38,6 +41,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
   for (int d = lane; d < D; d += 32) {
     const float v = __fdiv_rn(y[d], den);
     Yn[row * D + d] = v;
+    if (h16 != nullptr) h16[row * D + d] = __float2half_rn(v);
     if (hi != nullptr) {
       const float h = to_tf32(v);
       hi[row * D + d] = h;
@@ -436,11 +440,12 @@ knn_exact_rows_kernel(const float* __restrict__ Yq, const float* __restrict__ Ya
 
 // ---------------------------------------------------------------- host launchers
 int launch_normalize(const float* Y, int64_t rows, int D, float* Yn, float* hi, float* lo,
-                     cudaStream_t st) {
+                     cudaStream_t st, void* h16) {
   if (rows == 0) return OSC_OK;
   const int warps = 8;
   const int64_t blocks = (rows + warps - 1) / warps;
-  normalize_rows_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(Y, rows, D, Yn, hi, lo);
+  normalize_rows_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(Y, rows, D, Yn, hi, lo,
+                                                                  reinterpret_cast<__half*>(h16));
   OSC_LAUNCH_CHECK("normalize_rows_kernel");
   return OSC_OK;
 }

@@ -369,11 +369,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant
 //   tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogues of
 //   both CTAs arrive on the leader's "accumulator drained" barrier.
 //
-// ONEPASS = true: the single-product engine (OSC_KNN_TC1).  Only the tf32-rounded operands are
-// staged and ONE MMA is issued per K=8 step (a third of the tensor work, half of the staging
-// traffic per k-block, twice the pipeline depth).  Its scores carry the full TF32 operand error
-// (<= 2^-10 for unit rows); they only pre-select candidates -- the final sets and weights come from
-// the exact re-scoring, and the completeness check uses that error as a rigorous bound.
+// ONEPASS = true: the single-product engines.  Only the rounded operands are staged and ONE MMA is
+// issued per K step (a third of the tensor work, half of the staging traffic per k-block, twice the
+// pipeline depth).  The scores carry the full operand rounding error (<= 2^-10 for unit rows); they
+// only pre-select candidates -- the final sets and weights come from the exact re-scoring, and the
+// completeness check uses that error as a rigorous bound.
+//   F16 = false (OSC_KNN_TC1): tf32-rounded fp32 operands, kind::tf32, K = 8 per MMA.
+//   F16 = true  (OSC_KNN_TCH): fp16 operands, kind::f16, K = 16 per MMA.  fp16 carries the same 11
+//     significant bits as tf32, and the entries of a unit row sit in its normal range (|x| <= 1; below
+//     2^-14 the absolute error is <= 2^-25), so the error bound is the same -- at half the operand
+//     bytes (the kernel is bound by L2 -> shared-memory traffic at N ~ 1e3) and twice the MMA rate
+//     (it is tensor-bound at N ~ 1e6).  A 128-byte swizzle row holds 64 halves instead of 32 floats;
+//     the stage layout in BYTES, the descriptors and the +32 B K-step are unchanged.
 constexpr int TC2_HALF_BYTES = 128 * TC_BK * 4;                     // 128 rows x 32 floats
 template <bool ONEPASS>
 struct Tc2Cfg {
@@ -414,6 +421,17 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                                  uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -426,13 +444,15 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
       : "memory");
 }
 
-template <int KC, bool ONEPASS>
+template <int KC, bool ONEPASS, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                TcParams P) {
+  static_assert(!F16 || ONEPASS, "the fp16 engine is single-product");
   constexpr int TC2_STAGES = Tc2Cfg<ONEPASS>::STAGES;
   constexpr int TC2_STAGE_BYTES = Tc2Cfg<ONEPASS>::STAGE_BYTES;
+  constexpr int KE = F16 ? 64 : TC_BK;  // elements per 128-byte swizzle row = per k-block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -486,8 +506,8 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             const uint32_t fb = mapa_rank(full0 + 8 * p.stage, 0);   // the leader's full barrier
             if (leader) mbar_expect_tx(full0 + 8 * p.stage, 2 * TC2_STAGE_BYTES);
             if constexpr (ONEPASS) {
-              tma_load_3d_pair(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
-              tma_load_3d_pair(&tm_a_hi, sb + TC2_HALF_BYTES, fb, kb * TC_BK, n0, b);
+              tma_load_3d_pair(&tm_q_hi, sb, fb, kb * KE, m0, b);
+              tma_load_3d_pair(&tm_a_hi, sb + TC2_HALF_BYTES, fb, kb * KE, n0, b);
             } else {
               tma_load_3d_pair(&tm_q_hi, sb, fb, kb * TC_BK, m0, b);
               tma_load_3d_pair(&tm_q_lo, sb + TC2_HALF_BYTES, fb, kb * TC_BK, m0, b);
@@ -503,7 +523,9 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     // ===================== MMA issuer (leader CTA only)
     if (leader) {
       // instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=256 (pair)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+      // (fp16 engine: A = B = F16, format code 0)
+      const uint32_t fmt = F16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                              ((uint32_t)(256 >> 4) << 24);
       Pipe p, acc;
       for (int64_t w = pair; w < P.total_work; w += n_pairs) {
@@ -521,7 +543,8 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
 #pragma unroll
                 for (int ks = 0; ks < TC_BK / 8; ++ks) {
                   const uint64_t o = (uint64_t)((ks * 32) >> 4);
-                  tc_mma_tf32_pair(tacc, ah + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
+                  if constexpr (F16) tc_mma_f16_pair(tacc, ah + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
+                  else tc_mma_tf32_pair(tacc, ah + o, bh + o, idesc, (kb | ks) ? 1u : 0u);
                 }
               } else {
                 const uint64_t ah = umma_desc(sb), al = umma_desc(sb + TC2_HALF_BYTES),
@@ -619,15 +642,18 @@ static EncodeTiledFn encoder() {
   return fn;
 }
 
-// [batch][rows][D] fp32, box = {32 floats, box_rows, 1}, SWIZZLE_128B, OOB -> 0
-static int make_map(CUtensorMap* m, const float* ptr, int64_t batch, int64_t rows, int D, int box_rows) {
+// [batch][rows][D] fp32 (or fp16), box = {128 bytes of K, box_rows, 1}, SWIZZLE_128B, OOB -> 0
+static int make_map(CUtensorMap* m, const void* ptr, int64_t batch, int64_t rows, int D, int box_rows,
+                    bool f16 = false) {
   EncodeTiledFn enc = encoder();
   if (enc == nullptr) return fail(OSC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t esz = f16 ? 2 : 4;
   const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)batch};
-  const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)rows * D * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  const cuuint64_t strides[2] = {(cuuint64_t)D * esz, (cuuint64_t)rows * D * esz};
+  const cuuint32_t box[3] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box,
+  const CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                         const_cast<void*>(ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OSC_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
@@ -646,11 +672,17 @@ int knn_tc_supported(int64_t N, int D, int kc) {
 int knn_tc1_supported(int64_t n_rows, int64_t N, int D, int kc) {
   return knn_tc_supported(N, D, kc) && n_rows > TC_BM && sm_count() >= 2;
 }
+// fp16 operands: the row pitch D * 2 B must be a multiple of 16 B for the tensor map
+int knn_tch_supported(int64_t n_rows, int64_t N, int D, int kc) {
+  return knn_tc1_supported(n_rows, N, D, kc) && D % 8 == 0;
+}
 
+// f16 (single-product only): q_hi / all_hi point at fp16 arrays of the same [batch][rows][D] shape
 int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, const float* all_lo,
                   int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
-                  int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st) {
+                  int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st, bool f16) {
   if (!knn_tc_supported(N, D, kc)) return fail(OSC_ERR_UNSUPPORTED, "knn_tc: shape not covered");
+  OSC_REQUIRE(!f16 || (onepass && D % 8 == 0), "knn_tch: fp16 engine is single-product and needs D % 8 == 0");
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (onepass) {  // the lo parts are not read (the caller may pass NULL)
     OSC_REQUIRE(knn_tc1_supported(n_rows, N, D, kc), "knn_tc1: needs more than 128 query rows");
@@ -667,10 +699,10 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
   }
   CUtensorMap mqh, mql, mah, mal;
   int rc;
-  if ((rc = make_map(&mqh, q_hi, batch, n_rows, D, TC_BM))) return rc;
-  if ((rc = make_map(&mql, q_lo, batch, n_rows, D, TC_BM))) return rc;
-  if ((rc = make_map(&mah, all_hi, batch, N, D, pair ? 128 : TC_BN))) return rc;
-  if ((rc = make_map(&mal, all_lo, batch, N, D, pair ? 128 : TC_BN))) return rc;
+  if ((rc = make_map(&mqh, q_hi, batch, n_rows, D, TC_BM, f16))) return rc;
+  if ((rc = make_map(&mql, q_lo, batch, n_rows, D, TC_BM, f16))) return rc;
+  if ((rc = make_map(&mah, all_hi, batch, N, D, pair ? 128 : TC_BN, f16))) return rc;
+  if ((rc = make_map(&mal, all_lo, batch, N, D, pair ? 128 : TC_BN, f16))) return rc;
   TcParams P;
   P.batch = batch;
   P.n_rows = n_rows;
@@ -680,7 +712,7 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
   P.kc = kc;
   P.panels = (int)((n_rows + (pair ? 256 : TC_BM) - 1) / (pair ? 256 : TC_BM));
   P.col_tiles = (int)((N + TC_BN - 1) / TC_BN);
-  P.k_blocks = (D + TC_BK - 1) / TC_BK;
+  P.k_blocks = f16 ? (D + 63) / 64 : (D + TC_BK - 1) / TC_BK;
   P.total_work = batch * P.panels;
   P.cand_idx = cand_idx;
   P.cand_sim = cand_sim;
@@ -688,13 +720,17 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
     int64_t pairs = sms / 2;
     if (P.total_work < pairs) pairs = P.total_work;
     const unsigned grid = (unsigned)(2 * pairs);
-#define OSC_TC2_LAUNCH(K, OP)                                                                              \
+#define OSC_TC2_LAUNCH(K, ...)                                                                             \
   do {                                                                                                     \
-    OSC_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<K, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                  TC2_SMEM));                                                              \
-    knn_tc2_kernel<K, OP><<<grid, TC_THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);                        \
+    OSC_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<K, __VA_ARGS__>,                                            \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));                 \
+    knn_tc2_kernel<K, __VA_ARGS__><<<grid, TC_THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);               \
   } while (0)
-    if (onepass) {
+    if (f16) {
+      if (kc <= 16) OSC_TC2_LAUNCH(16, true, true);
+      else if (kc <= 24) OSC_TC2_LAUNCH(24, true, true);
+      else OSC_TC2_LAUNCH(32, true, true);
+    } else if (onepass) {
       if (kc <= 16) OSC_TC2_LAUNCH(16, true);
       else if (kc <= 24) OSC_TC2_LAUNCH(24, true);
       else OSC_TC2_LAUNCH(32, true);

@@ -404,12 +404,16 @@ class ShardedLattice:
         if N >= 2:
             eng, kc, eps = cabi.knn_plan(max(self.n_local, 1), N, D, k, self._engine)
             use_tc = eng in (cabi.KNN_TC, cabi.KNN_TC1)
-            self.engine_used = {cabi.KNN_SIMT: "simt", cabi.KNN_TC: "tc", cabi.KNN_TC1: "tc1"}[eng]
+            self.engine_used = cabi.ENGINE_NAMES[eng]
             Yn = torch.empty_like(Y_all)
             hi = torch.empty_like(Y_all) if use_tc else None
             lo = torch.empty_like(Y_all) if eng == cabi.KNN_TC else None
             P = cabi.ptr
-            cabi.check(lib.osc_normalize_rows(Y_all.data_ptr(), N, D, Yn.data_ptr(), P(hi), P(lo), st))
+            if eng == cabi.KNN_TCH:  # fp16 rows ride in the q_hi / all_hi arguments
+                hi = torch.empty(Y_all.shape, dtype=torch.float16, device=dev)
+                cabi.check(lib.osc_normalize_rows_f16(Y_all.data_ptr(), N, D, Yn.data_ptr(), hi.data_ptr(), st))
+            else:
+                cabi.check(lib.osc_normalize_rows(Y_all.data_ptr(), N, D, Yn.data_ptr(), P(hi), P(lo), st))
             nl, r0 = self.n_local, self.row0
             cand_idx = torch.empty((max(nl, 1), kc), dtype=torch.int32, device=dev)
             cand_sim = torch.empty((max(nl, 1), kc), dtype=torch.float32, device=dev)
@@ -417,8 +421,7 @@ class ShardedLattice:
             top_sim = torch.zeros((max(nl, 1), k), dtype=torch.float32, device=dev)
             gap = torch.empty(max(nl, 1), dtype=torch.float32, device=dev)
             if nl > 0:
-                off = r0 * D * 4
-                q = lambda t: None if t is None else t.data_ptr() + off  # noqa: E731
+                q = lambda t: None if t is None else t.data_ptr() + r0 * D * t.element_size()  # noqa: E731
                 cabi.check(lib.osc_knn_candidates(
                     q(Yn), Yn.data_ptr(), q(hi), q(lo), P(hi), P(lo), 1, nl, r0, N, D, kc,
                     eng, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st), "osc_knn_candidates")

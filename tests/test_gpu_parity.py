@@ -276,6 +276,9 @@ def test_tc_and_simt_engines_build_identical_graphs(shape):
     if N > 128:  # the single-product engine is a 2-CTA kernel: more than one 128-row panel
         engines.append(("tc1", _cabi.KNN_TC1))
         assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TC1)[2] == pytest.approx(1e-3)
+        if D % 8 == 0:  # fp16 single-product engine
+            engines.append(("tch", _cabi.KNN_TCH))
+            assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TCH)[2] == pytest.approx(1e-3)
     for name, eng in engines:
         nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev)
         A = torch.empty((B, N, k), dtype=torch.float32, device=dev)
@@ -299,6 +302,7 @@ def test_tc_and_simt_engines_build_identical_graphs(shape):
 
 
 @pytest.mark.parametrize("shape,eng_name", [((2, 1200, 384, 8), "tc"), ((2, 1200, 384, 8), "tc1"),
+                                            ((2, 1200, 384, 8), "tch"), ((1, 700, 72, 10), "tch"),
                                             ((1, 700, 64, 10), "tc1"), ((1, 300, 32, 6), "simt")])
 def test_pruned_rescoring_equals_full_rescoring(shape, eng_name):
     """osc_knn_rescore_checked skips candidates that the engine's error bound proves to lie below the
@@ -315,19 +319,28 @@ def test_pruned_rescoring_equals_full_rescoring(shape, eng_name):
     gen = torch.Generator(device=dev)
     gen.manual_seed(7 * N + D)
     Y = torch.randn((B, N, D), generator=gen, device=dev)
-    flags = {"simt": _cabi.KNN_SIMT, "tc": _cabi.KNN_TC, "tc1": _cabi.KNN_TC1}[eng_name]
+    flags = {"simt": _cabi.KNN_SIMT, "tc": _cabi.KNN_TC, "tc1": _cabi.KNN_TC1, "tch": _cabi.KNN_TCH}[eng_name]
     eng, kc, eps = _cabi.knn_plan(N, N, D, k, flags)
     assert eng == flags and kc >= k + 4
     st = torch.cuda.current_stream().cuda_stream
     Yn, hi, lo = torch.empty_like(Y), torch.empty_like(Y), torch.empty_like(Y)
-    _cabi.check(lib.osc_normalize_rows(Y.data_ptr(), B * N, D, Yn.data_ptr(), hi.data_ptr(),
-                                       lo.data_ptr() if eng == _cabi.KNN_TC else None, st))
+    if eng == _cabi.KNN_TCH:
+        hi = torch.empty(Y.shape, dtype=torch.float16, device=dev)
+        _cabi.check(lib.osc_normalize_rows_f16(Y.data_ptr(), B * N, D, Yn.data_ptr(), hi.data_ptr(), st))
+        assert torch.equal(hi, Yn.to(torch.float16)), "fp16 rows = round-to-nearest of Yn"
+    else:
+        _cabi.check(lib.osc_normalize_rows(Y.data_ptr(), B * N, D, Yn.data_ptr(), hi.data_ptr(),
+                                           lo.data_ptr() if eng == _cabi.KNN_TC else None, st))
     ci = torch.empty((B, N, kc), dtype=torch.int32, device=dev)
     cs = torch.empty((B, N, kc), dtype=torch.float32, device=dev)
     _cabi.check(lib.osc_knn_candidates(Yn.data_ptr(), Yn.data_ptr(), hi.data_ptr(), lo.data_ptr(), hi.data_ptr(),
                                        lo.data_ptr(), B, N, 0, N, D, kc, eng, ci.data_ptr(), cs.data_ptr(),
                                        None, 0, st), "candidates")
     assert bool((cs[..., :-1] >= cs[..., 1:]).all()), "candidate lists must be sorted descending"
+    # the engine's scores stay within the error bound the completeness check relies on
+    exact = torch.gather(Yn.double() @ Yn.double().transpose(1, 2), 2, ci.clamp(min=0).long())
+    err = float(((cs.double() - exact).abs() * (ci >= 0)).max())
+    assert err <= eps, (eng_name, err, eps)
     out = {}
     for mode in ("full", "pruned"):
         ti = torch.empty((B, N, k), dtype=torch.int32, device=dev)
