@@ -266,11 +266,13 @@ def run_ours(args) -> None:
     if dom == "knn_candidates":
         flops = 2.0 * N_LAT * N_LAT * D_LAT * B  # 2 N^2 D per lattice
         achieved = flops / (kern_ms[dom] / 1000.0) / 1e12
-        # TF32 tensor rate is half the bf16 rate; denominator derived from the measured bf16 peak
-        peak = 0.5 * float(peaks["bf16_tflops_sustained"])
+        # fp16 engine: the measured bf16 rate; TF32 engines: half of it
+        half = engine != "tch"
+        peak = (0.5 if half else 1.0) * float(peaks["bf16_tflops_sustained"])
         roof = {"kernel": "knn_candidates(" + engine + ")", "bound": "tensor", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": f"{peak_src}: 0.5 x bf16_tflops_sustained (TF32 = half bf16 rate)",
+                "peak_source": f"{peak_src}: " + ("0.5 x bf16_tflops_sustained (TF32 = half bf16 rate)" if half
+                                                  else "bf16_tflops_sustained (fp16 operands)"),
                 "algorithmic": "2*N^2*D flops per lattice (3xTF32 issues 3x that on the tensor pipe)"}
     else:
         V = N_LAT * D_LAT * 4.0
@@ -297,8 +299,32 @@ def run_ours(args) -> None:
     except Exception:
         pass
     if dom == "batched_settle":
-        roof["note"] = ("everything but Y in / U out stays on chip, so HBM is not the binding resource: ncu shows "
-                        "LDS-latency (short scoreboard) stalls, shared-memory pipe 58 % busy -- profiles/README.md")
+        # What binds this kernel is the shared-memory data pipe, not HBM: p (the gathered vector) and the
+        # graph image live in shared memory.  Algorithmic shared-memory bytes per lattice:
+        # every gather pass moves Np*kp*(16 B of p + 6 B of graph) per 4-column slab, every CG iteration
+        # re-reads and re-writes the thread's own rows of p (Np * 32 B).
+        it_s, it_u = check["iters_mean"], check["ustar_iters_mean"]
+        Np, kp, G = 1280, (K_LAT + 3) // 4 * 4, D_LAT // 4
+        passes = it_s + it_u + 1.0          # one gather pass over Y serves both initial residuals
+        smem_bytes = G * (passes * Np * kp * 22.0 + (it_s + it_u) * Np * 32.0) * B
+        sm_clk = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        smem_peak = 148 * 128.0 * sm_clk / 1e9   # 128 B per clock per SM
+        onchip = {"bound": "smem", "achieved": smem_bytes / (kern_ms[dom] / 1000.0) / 1e9, "peak": smem_peak,
+                  "unit": "GB/s", "algorithmic": "G*((it_s+it_u+1)*Np*kp*22 + (it_s+it_u)*Np*32) bytes per lattice, "
+                  "conflict-free; peak = 148 SMs x 128 B/clk x sampled SM clock"}
+        onchip["frac"] = onchip["achieved"] / onchip["peak"]
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f).get(dom) or {}
+            if "l1tex_data_pipe_pct" in tr:
+                onchip["ncu_l1tex_data_pipe_pct"] = tr["l1tex_data_pipe_pct"]
+                onchip["ncu_source"] = tr.get("l1tex_source")
+        except Exception:
+            pass
+        roof["onchip"] = onchip
+        roof["note"] = ("everything but Y in / U out stays on chip, so HBM is not the binding resource; the "
+                        "binding unit is the L1TEX/shared-memory data pipe (see `onchip`; the ncu capture counts "
+                        "bank-conflict and reduction wavefronts on top of the algorithmic bytes)")
     roof["kernel_ms_per_step"] = kern_ms
     roof["share_of_step"] = {k: v / (ms / args.steps) for k, v in kern_ms.items()}
 
@@ -334,7 +360,7 @@ def run_ours(args) -> None:
         # builds in seconds; N=10M and the multi-GPU runs (--workload large) are under profiles/
         del Y, Y_host
         torch.cuda.empty_cache()
-        big = measure_large(args.N, args.D, args.k, steps=2, warmup=1, partition="rows", world=1, rank=0,
+        big = measure_large(args.N, args.D, args.k, steps=3, warmup=3, partition="rows", world=1, rank=0,
                             local=local)
         line["large_lattice"] = {k: big[k] for k in ("metric", "value", "unit", "n_gpus", "config", "roofline",
                                                      "build_ms", "receipt_light_ms", "check")}
