@@ -246,6 +246,8 @@ def run_ours(args) -> None:
     bl, _ = step_resident()
     engine = getattr(bl, "engine_used", "simt")
     nnz_mean = float(bl.nnz.double().mean().item())
+    check["knn_candidate_width"] = int(getattr(bl, "kc", 0))
+    check["rows_recomputed_exhaustively_per_step"] = int(bl.n_exhaustive.item()) if hasattr(bl, "n_exhaustive") else 0
     del bl
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
