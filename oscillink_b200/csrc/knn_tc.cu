@@ -387,7 +387,7 @@ struct Tc2Cfg {
   static constexpr int STAGES = ONEPASS ? 6 : 3;
   static constexpr int STAGE_BYTES = (ONEPASS ? 2 : 4) * TC2_HALF_BYTES;  // Ahi [Alo] Bhi(half) [Blo(half)]
 };
-constexpr int TC2_SMEM = 3 * 4 * TC2_HALF_BYTES + 1024 + 256 + TC_EPI_BYTES;  // same for both configs
+constexpr int TC2_SMEM = 3 * 4 * TC2_HALF_BYTES + 1024 + 256 + 2 * TC_EPI_BYTES;  // same for all configs (8 chunk buffers)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -444,8 +444,13 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
       : "memory");
 }
 
-template <int KC, bool ONEPASS, bool F16 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+// EW = epilogue warps per CTA (4 or 8).  With 8, two warps share every TMEM lane quarter (warp w and
+// w + 4 address the same 32 lanes) and take alternate 32-column chunks of every tile, each with its own
+// register top-KC list; the lists are merged through shared memory once per row panel.  At N ~ 1e3 the
+// epilogue (about KC*(1+ln(N/KC)) list insertions per row) bounds the kernel, and a single warp per
+// scheduler cannot hide its own LDS / vote latencies between insertion rounds.
+template <int KC, bool ONEPASS, bool F16 = false, int EW = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                TcParams P) {
@@ -476,7 +481,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 256);  // 128 epilogue threads of each CTA (used in the leader only)
+      mbar_init(tempty0 + 8 * a, 64 * EW);  // every epilogue thread of both CTAs (used in the leader only)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -569,9 +574,12 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     }
   } else {
     // ===================== epilogue: fused per-row top-KC on this CTA's 128 rows
-    const int quarter = warp & 3;
+    static_assert(EW == 4 || (EW == 8 && KC <= 16), "the list merge parks KC values + KC indices in 32 words per lane");
+    const int ew = warp - 2;       // 0..EW-1
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read (hardware: warp id % 4)
+    const int half = ew >> 2;      // EW == 8: 0 takes the even chunks of a tile, 1 the odd ones
     const int r_tile = quarter * 32 + lane;
-    float* ebuf = reinterpret_cast<float*>(gen_base + TC2_STAGES * TC2_STAGE_BYTES + 256) + quarter * 1024;
+    float* ebuf = reinterpret_cast<float*>(gen_base + TC2_STAGES * TC2_STAGE_BYTES + 256) + ew * 1024;
     const uint32_t tempty_leader0 = mapa_rank(tempty0, 0);
     Pipe acc;
     for (int64_t w = pair; w < P.total_work; w += n_pairs) {
@@ -593,7 +601,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc.stage * TC_BN);
 #pragma unroll 1
-        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+        for (int ch = (EW == 8 ? half : 0); ch < TC_BN / 32; ch += (EW == 8 ? 2 : 1)) {
           const int c0 = n0 + ch * 32;
           if (c0 >= P.N) break;  // warp-uniform
           float v[32];
@@ -604,7 +612,28 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         mbar_arrive_cluster(tempty_leader0 + 8 * acc.stage);
         acc.advance(2);
       }
-      if (row_ok) {
+      if constexpr (EW == 8) {
+        // merge the partner warp's list (same rows, the other chunks): parked in ITS chunk buffer
+        float* pbuf = half ? ebuf : ebuf + 4 * 1024;
+        if (half) {
+#pragma unroll
+          for (int i = 0; i < KC; ++i) {
+            pbuf[i * 32 + lane] = val[i];
+            pbuf[(16 + i) * 32 + lane] = __int_as_float(idx[i]);
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (!half) {
+#pragma unroll 1
+          for (int i = 0; i < KC; ++i) {
+            const float sv = pbuf[i * 32 + lane];
+            const int sj = __float_as_int(pbuf[(16 + i) * 32 + lane]);
+            if (sv > val[KC - 1]) topk_insert<KC>(val, idx, sv, sj);
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // pbuf is a chunk buffer again
+      }
+      if (row_ok && half == 0) {
         const int64_t o = (b * P.n_rows + gi) * P.kc;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
@@ -720,13 +749,22 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
     int64_t pairs = sms / 2;
     if (P.total_work < pairs) pairs = P.total_work;
     const unsigned grid = (unsigned)(2 * pairs);
-#define OSC_TC2_LAUNCH(K, ...)                                                                             \
+#define OSC_TC2_LAUNCH_T(THREADS, K, ...)                                                                  \
   do {                                                                                                     \
     OSC_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<K, __VA_ARGS__>,                                            \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));                 \
-    knn_tc2_kernel<K, __VA_ARGS__><<<grid, TC_THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);               \
+    knn_tc2_kernel<K, __VA_ARGS__><<<grid, THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);                  \
   } while (0)
-    if (f16) {
+#define OSC_TC2_LAUNCH(K, ...) OSC_TC2_LAUNCH_T(TC_THREADS, K, __VA_ARGS__)
+    // small lattices: the top-k epilogue bounds the kernel -> 8 epilogue warps (dev switch OSC_KNN_EW=4)
+    bool ew8 = f16 && kc <= 16 && N <= 8192;
+    {
+      const char* e = getenv("OSC_KNN_EW");
+      if (e && atoi(e) == 4) ew8 = false;
+    }
+    if (ew8) {
+      OSC_TC2_LAUNCH_T(64 + 32 * 8, 16, true, true, 8);
+    } else if (f16) {
       if (kc <= 16) OSC_TC2_LAUNCH(16, true, true);
       else if (kc <= 24) OSC_TC2_LAUNCH(24, true, true);
       else OSC_TC2_LAUNCH(32, true, true);
@@ -740,6 +778,7 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
     else if (kc <= 24) OSC_TC2_LAUNCH(24, false);
     else OSC_TC2_LAUNCH(32, false);
 #undef OSC_TC2_LAUNCH
+#undef OSC_TC2_LAUNCH_T
     OSC_LAUNCH_CHECK("knn_tc2_kernel");
     return OSC_OK;
   }
