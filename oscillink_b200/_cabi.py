@@ -20,7 +20,7 @@ KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC1, KNN_TCH = 0, 1, 2, 3, 4
 ENGINE_NAMES = {KNN_SIMT: "simt", KNN_TC: "tc", KNN_TC1: "tc1", KNN_TCH: "tch"}
 MODE_SETTLE, MODE_STATIONARY = 0, 1
 KNN_EPS = 1e-5  # OSC_KNN_EPS
-KNN_EPS_TC1 = 1e-3  # OSC_KNN_EPS_TC1
+KNN_EPS_TC1 = 1.25e-3  # OSC_KNN_EPS_TC1
 
 c_i32, c_i64, c_f32, c_f64, c_void_p, c_size_t = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_size_t
 

@@ -20,6 +20,7 @@
 // neighbour sets in the canonical order -- both engines therefore yield identical graphs.
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -195,6 +196,64 @@ __device__ __forceinline__ void topk_chunk(float (&val)[KC], int (&idx)[KC], flo
       mask &= mask - 1;
       const float s = buf[e * 32 + lane];
       if (s > val[KC - 1]) topk_insert<KC>(val, idx, s, c0 + e);
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- packed-key top-KC (N <= 2048)
+// For small lattices the epilogue, not the tensor pipe, bounds the kernel (profiles/
+// r01_knn_tch_ncu_summary.txt: 0.25 IPC on the epilogue warps, predicate-chained selects).  With the
+// column index in the low 11 bits of an order-preserving integer image of the score, a list entry is ONE
+// register and the sorted insertion is a branch-free, predicate-free min/max network:
+//     new[q] = max(old[q], min(old[q-1], key))        (2 IMNMX per slot, all slots independent)
+// Keys order by (score truncated to 21 bits desc, column asc).  The truncation costs <= 2^-12 relative
+// (2.5e-4 absolute for unit rows); OSC_KNN_EPS_TC1 covers it next to the 2^-10 operand rounding.
+constexpr int PK_COL_BITS = 11;
+constexpr int PK_COL_MASK = (1 << PK_COL_BITS) - 1;
+__device__ __forceinline__ int pk_key(float s, int col) {
+  const int b = __float_as_int(s);
+  const int t = b ^ ((b >> 31) & 0x7fffffff);  // monotone under signed compare
+  return (t & ~PK_COL_MASK) | (PK_COL_MASK - col);
+}
+__device__ __forceinline__ float pk_score(int key) {
+  const int t = key & ~PK_COL_MASK;
+  return __int_as_float(t ^ ((t >> 31) & 0x7fffffff));
+}
+__device__ __forceinline__ int pk_col(int key) { return PK_COL_MASK - (key & PK_COL_MASK); }
+
+template <int KC>
+__device__ __forceinline__ void pk_insert(int (&key)[KC], int k) {
+#pragma unroll
+  for (int q = KC - 1; q > 0; --q) key[q] = max(key[q], min(key[q - 1], k));
+  key[0] = max(key[0], k);
+}
+
+template <int KC>
+__device__ __forceinline__ void pk_chunk(int (&key)[KC], float (&v)[32], int c0, int N, int self, bool row_ok,
+                                         float* buf, int lane) {
+  const bool self_here = __any_sync(0xffffffffu, self >= c0 && self < c0 + 32);
+  if (c0 + 32 > N || self_here) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i >= N || c0 + i == self) v[i] = -INFINITY;
+  }
+  // the truncated score of the last entry is <= its true score: a few extra hits, never a missed one
+  const float thr = key[KC - 1] == INT_MIN ? -INFINITY : pk_score(key[KC - 1]);
+  unsigned mask = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (v[i] > thr) mask |= 1u << i;
+  if (!row_ok) mask = 0;
+  if (!__any_sync(0xffffffffu, mask != 0)) return;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) buf[i * 32 + lane] = v[i];
+  __syncwarp();
+  while (__any_sync(0xffffffffu, mask != 0)) {
+    if (mask != 0) {
+      const int e = __ffs(mask) - 1;
+      mask &= mask - 1;
+      pk_insert<KC>(key, pk_key(buf[e * 32 + lane], c0 + e));
     }
   }
   __syncwarp();
@@ -449,7 +508,7 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
 // register top-KC list; the lists are merged through shared memory once per row panel.  At N ~ 1e3 the
 // epilogue (about KC*(1+ln(N/KC)) list insertions per row) bounds the kernel, and a single warp per
 // scheduler cannot hide its own LDS / vote latencies between insertion rounds.
-template <int KC, bool ONEPASS, bool F16 = false, int EW = 4>
+template <int KC, bool ONEPASS, bool F16 = false, int EW = 4, bool PACKED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -588,12 +647,13 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
       const int gi = m0 + r_tile;
       const int self = (int)(P.row0 + gi);
       const bool row_ok = gi < P.n_rows;
-      float val[KC];
+      // PACKED: one register per entry (pk_key); otherwise separate score / column lists
+      float val[PACKED ? 1 : KC];
       int idx[KC];
 #pragma unroll
       for (int i = 0; i < KC; ++i) {
-        val[i] = -INFINITY;
-        idx[i] = -1;
+        if constexpr (!PACKED) val[i] = -INFINITY;
+        idx[i] = PACKED ? INT_MIN : -1;
       }
       for (int ct = 0; ct < P.col_tiles; ++ct) {
         const int n0 = ct * TC_BN;
@@ -606,7 +666,8 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
           if (c0 >= P.N) break;  // warp-uniform
           float v[32];
           tmem_ld32(trow + (uint32_t)(ch * 32), v);
-          topk_chunk<KC>(val, idx, v, c0, (int)P.N, self, row_ok, ebuf, lane);
+          if constexpr (PACKED) pk_chunk<KC>(idx, v, c0, (int)P.N, self, row_ok, ebuf, lane);
+          else topk_chunk<KC>(val, idx, v, c0, (int)P.N, self, row_ok, ebuf, lane);
         }
         tc_fence_before();
         mbar_arrive_cluster(tempty_leader0 + 8 * acc.stage);
@@ -618,7 +679,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         if (half) {
 #pragma unroll
           for (int i = 0; i < KC; ++i) {
-            pbuf[i * 32 + lane] = val[i];
+            if constexpr (!PACKED) pbuf[i * 32 + lane] = val[i];
             pbuf[(16 + i) * 32 + lane] = __int_as_float(idx[i]);
           }
         }
@@ -626,9 +687,13 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         if (!half) {
 #pragma unroll 1
           for (int i = 0; i < KC; ++i) {
-            const float sv = pbuf[i * 32 + lane];
             const int sj = __float_as_int(pbuf[(16 + i) * 32 + lane]);
-            if (sv > val[KC - 1]) topk_insert<KC>(val, idx, sv, sj);
+            if constexpr (PACKED) {
+              pk_insert<KC>(idx, sj);
+            } else {
+              const float sv = pbuf[i * 32 + lane];
+              if (sv > val[KC - 1]) topk_insert<KC>(val, idx, sv, sj);
+            }
           }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // pbuf is a chunk buffer again
@@ -638,8 +703,14 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
           if (i < P.kc) {
-            P.cand_idx[o + i] = idx[i];
-            P.cand_sim[o + i] = val[i];
+            if constexpr (PACKED) {
+              const bool empty = idx[i] == INT_MIN;
+              P.cand_idx[o + i] = empty ? -1 : pk_col(idx[i]);
+              P.cand_sim[o + i] = empty ? -INFINITY : pk_score(idx[i]);
+            } else {
+              P.cand_idx[o + i] = idx[i];
+              P.cand_sim[o + i] = val[i];
+            }
           }
         }
       }
@@ -764,8 +835,19 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
       const char* e = getenv("OSC_KNN_EW");
       if (e && atoi(e) == 8) ew8 = f16 && kc <= 16;
     }
+    // packed-key lists: single-product engines, the column index must fit 11 bits (OSC_KNN_PACKED=0: off)
+    bool packed = onepass && kc <= 16 && N <= (1 << PK_COL_BITS);
+    {
+      const char* e = getenv("OSC_KNN_PACKED");
+      if (e && atoi(e) == 0) packed = false;
+    }
     if (ew8) {
-      OSC_TC2_LAUNCH_T(64 + 32 * 8, 16, true, true, 8);
+      if (packed) OSC_TC2_LAUNCH_T(64 + 32 * 8, 16, true, true, 8, true);
+      else OSC_TC2_LAUNCH_T(64 + 32 * 8, 16, true, true, 8);
+    } else if (packed && f16) {
+      OSC_TC2_LAUNCH(16, true, true, 4, true);
+    } else if (packed) {
+      OSC_TC2_LAUNCH(16, true, false, 4, true);
     } else if (f16) {
       if (kc <= 16) OSC_TC2_LAUNCH(16, true, true);
       else if (kc <= 24) OSC_TC2_LAUNCH(24, true, true);

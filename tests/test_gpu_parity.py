@@ -275,10 +275,10 @@ def test_tc_and_simt_engines_build_identical_graphs(shape):
     engines = [("simt", _cabi.KNN_SIMT), ("tc", _cabi.KNN_TC)]
     if N > 128:  # the single-product engine is a 2-CTA kernel: more than one 128-row panel
         engines.append(("tc1", _cabi.KNN_TC1))
-        assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TC1)[2] == pytest.approx(1e-3)
+        assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TC1)[2] == pytest.approx(1.25e-3)
         if D % 8 == 0:  # fp16 single-product engine
             engines.append(("tch", _cabi.KNN_TCH))
-            assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TCH)[2] == pytest.approx(1e-3)
+            assert _cabi.knn_plan(N, N, D, k, _cabi.KNN_TCH)[2] == pytest.approx(1.25e-3)
     for name, eng in engines:
         nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev)
         A = torch.empty((B, N, k), dtype=torch.float32, device=dev)
