@@ -827,19 +827,20 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
     knn_tc2_kernel<K, __VA_ARGS__><<<grid, THREADS, TC2_SMEM, st>>>(mqh, mql, mah, mal, P);                  \
   } while (0)
 #define OSC_TC2_LAUNCH(K, ...) OSC_TC2_LAUNCH_T(TC_THREADS, K, __VA_ARGS__)
-    // 8 epilogue warps (OSC_KNN_EW=8, opt-in): measured on B200 at 4096 x N=1200 it takes the kernel from
-    // 14.4 to 13.3 ms only -- every warp starts its own list from -inf, so the insertion rounds per warp
-    // fall by a quarter, not by half, and the total instruction count grows by 29 %.
-    bool ew8 = false;
-    {
-      const char* e = getenv("OSC_KNN_EW");
-      if (e && atoi(e) == 8) ew8 = f16 && kc <= 16;
-    }
     // packed-key lists: single-product engines, the column index must fit 11 bits (OSC_KNN_PACKED=0: off)
     bool packed = onepass && kc <= 16 && N <= (1 << PK_COL_BITS);
     {
       const char* e = getenv("OSC_KNN_PACKED");
       if (e && atoi(e) == 0) packed = false;
+    }
+    // 8 epilogue warps.  Measured on B200 at 4096 x N=1200 (fp16 engine): score/column lists 14.4 ms
+    // with 4 warps, 13.3 with 8 (each warp restarts its list from -inf: +29 % instructions); packed keys
+    // 11.2 ms with 4 warps, 9.5 ms with 8 -> default with packed keys.  OSC_KNN_EW=4 / 8 overrides.
+    bool ew8 = packed && f16;
+    {
+      const char* e = getenv("OSC_KNN_EW");
+      if (e && atoi(e) == 8) ew8 = f16 && kc <= 16;
+      if (e && atoi(e) == 4) ew8 = false;
     }
     if (ew8) {
       if (packed) OSC_TC2_LAUNCH_T(64 + 32 * 8, 16, true, true, 8, true);
