@@ -609,7 +609,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="lattices per step per GPU")
-    ap.add_argument("--chunk", type=int, default=256, help="lattices per H2D/compute pipeline stage (e2e)")
+    ap.add_argument("--chunk", type=int, default=128, help="lattices per H2D/compute pipeline stage (e2e)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="serving", choices=["serving", "large"],
                     help="serving: the headline batch of N=1200 lattices; large: one big lattice (ms/settle)")

@@ -263,7 +263,7 @@ class BatchedLattices:
 
 
 def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: int = 6, *,
-                      chunk: int = 256, max_iters: int = 12, tol: float = 1e-3, receipt: bool = True,
+                      chunk: int = 128, max_iters: int = 12, tol: float = 1e-3, receipt: bool = True,
                       out_host: torch.Tensor | None = None, device: torch.device | None = None,
                       **lattice_kw) -> torch.Tensor:
     """End-to-end serving call on HOST buffers: for every lattice b of Y_host[B,N,D] (pinned fp32)
