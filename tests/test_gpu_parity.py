@@ -366,6 +366,59 @@ def test_pruned_rescoring_equals_full_rescoring(shape, eng_name):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("N", [264, 2048, 2056])
+def test_packed_key_lists_handle_negative_scores_and_the_column_limit(N):
+    """The fp16 engine keeps (score image | column) keys in one register for N <= 2048 and score/column
+    lists above.  Near-simplex anchors make every similarity slightly NEGATIVE (-1/(N-1) + noise), which
+    exercises the sign handling of the key order; 2048 / 2056 straddle the 11-bit column limit.  The
+    scores are closer together than the engine's error bound, so the completeness check sends the rows
+    through the exhaustive kernel as well.  The canonical top-k after re-scoring must equal the
+    CUDA-core engine's, and the engine's scores must stay inside its error bound."""
+    import ctypes as C
+
+    import torch
+
+    from oscillink_b200 import _cabi
+
+    lib = _cabi.load()
+    dev = torch.device("cuda")
+    D, k = N, 6
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(N)
+    Y = (torch.eye(N, device=dev) - 1.0 / N + (0.1 / N) * torch.randn((N, D), generator=gen, device=dev))[None]
+    st = torch.cuda.current_stream().cuda_stream
+    tops = {}
+    for name, flags in (("simt", _cabi.KNN_SIMT), ("tch", _cabi.KNN_TCH)):
+        eng, kc, eps = _cabi.knn_plan(N, N, D, k, flags)
+        assert eng == flags
+        Yn = torch.empty_like(Y)
+        hi = torch.empty(Y.shape, dtype=torch.float16, device=dev)
+        _cabi.check(lib.osc_normalize_rows_f16(Y.data_ptr(), N, D, Yn.data_ptr(), hi.data_ptr(), st))
+        ci = torch.empty((1, N, kc), dtype=torch.int32, device=dev)
+        cs = torch.empty((1, N, kc), dtype=torch.float32, device=dev)
+        _cabi.check(lib.osc_knn_candidates(Yn.data_ptr(), Yn.data_ptr(), hi.data_ptr(), None, hi.data_ptr(), None,
+                                           1, N, 0, N, D, kc, eng, ci.data_ptr(), cs.data_ptr(), None, 0, st), name)
+        assert bool((ci >= 0).all()) and bool((cs[..., :-1] >= cs[..., 1:]).all())
+        exact = torch.gather(Yn.double() @ Yn.double().transpose(1, 2), 2, ci.long())
+        assert float((cs.double() - exact).abs().max()) <= eps, name
+        assert float(exact.max()) < 0.0  # the case really is all-negative
+        ti = torch.empty((1, N, k), dtype=torch.int32, device=dev)
+        ts = torch.empty((1, N, k), dtype=torch.float32, device=dev)
+        gap = torch.empty((1, N), dtype=torch.float32, device=dev)
+        nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+        need = C.c_size_t(0)
+        _cabi.check(lib.osc_knn_rescore_workspace(1, N, C.byref(need)))
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+        _cabi.check(lib.osc_knn_rescore_checked(Yn.data_ptr(), Yn.data_ptr(), 1, N, 0, N, D, ci.data_ptr(),
+                                                cs.data_ptr(), kc, k, eps, ti.data_ptr(), ts.data_ptr(),
+                                                gap.data_ptr(), nflag.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                    "rescore_checked")
+        torch.cuda.synchronize()
+        tops[name] = (ti.cpu().numpy(), ts.cpu().numpy())
+    assert np.array_equal(tops["simt"][0], tops["tch"][0])
+    assert np.array_equal(tops["simt"][1], tops["tch"][1])
+
+
 @pytest.mark.parametrize("name", ["quickstart_120", "readme_80", "config2_1200", "gates_300"])
 def test_bundle_matches_reference(api, name):
     """f1: bundle() ids identical, scores / alignments within 1e-4 (z-scores amplify fp32 noise)."""
