@@ -403,6 +403,11 @@ __device__ int slab_solve(Slab<TPT>& st, const SolveCoef& c, double tol, int max
 // row visits its neighbours is free, and padding slots (weight 0) may point at any row, so each
 // group of 8 rows greedily schedules its neighbour lists such that the residues met at every
 // step are distinct where possible (measured 1.34 wavefronts per gather at N=1200, k=8).
+// Tried and dropped (B200, B=1440): (a) an exact bipartite edge colouring of the visit order -- 1.38,
+// the residue imbalance inside a group (a residue met more than kp times) is what remains, not the
+// greedy order; (b) permuting rows inside their block of 8 so that every group meets the residues
+// evenly (1.12 in simulation): the slab kernel gained 3 % (20.0 -> 19.4 ms) but the balancing pass and
+// the position-indirect packer cost 1.6 ms more than the plain packer.
 __global__ void __launch_bounds__(128)
 batched_pack_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ W,
                     const int32_t* __restrict__ deg, int64_t batch, int N, int k, int kp,
