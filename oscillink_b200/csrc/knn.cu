@@ -370,34 +370,57 @@ knn_exact_rows_kernel(const float* __restrict__ Yq, const float* __restrict__ Ya
     const float* all = Yall + b * N * D;
     const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(yi) | reinterpret_cast<uintptr_t>(all)) % 16 == 0);
     int cnt = 0;
-    for (int64_t j = w; j < N; j += warps) {
-      if (j == self) continue;
-      const float* yj = all + j * D;
-      double acc = 0.0;
+    // four columns per step: their row fetches are independent (the scan is latency-bound), the four
+    // totals come out of one butterfly (bit-identical to warp_sum, see warp_sum4)
+    for (int64_t j0 = w; j0 < N; j0 += 4 * warps) {
+      int64_t jj[4];
+      const float* yj[4];
+      double acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        jj[u] = j0 + (int64_t)u * warps;
+        const bool ok = jj[u] < N && jj[u] != self;
+        if (!ok) jj[u] = -1;
+        yj[u] = ok ? all + jj[u] * D : yi;
+        acc[u] = 0.0;
+      }
       if (v4) {  // same element ownership / order per lane as knn_rescore_kernel: bit-identical scores
         for (int d = lane * 4; d < D; d += 128) {
           const float4 q = *reinterpret_cast<const float4*>(yi + d);
-          const float4 x = *reinterpret_cast<const float4*>(yj + d);
-          acc = fma((double)q.x, (double)x.x, acc);
-          acc = fma((double)q.y, (double)x.y, acc);
-          acc = fma((double)q.z, (double)x.z, acc);
-          acc = fma((double)q.w, (double)x.w, acc);
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(yj[u] + d);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[u] = fma((double)q.x, (double)x[u].x, acc[u]);
+            acc[u] = fma((double)q.y, (double)x[u].y, acc[u]);
+            acc[u] = fma((double)q.z, (double)x[u].z, acc[u]);
+            acc[u] = fma((double)q.w, (double)x[u].w, acc[u]);
+          }
         }
       } else {
-        for (int d = lane; d < D; d += 32) acc = fma((double)yi[d], (double)yj[d], acc);
-      }
-      acc = warp_sum(acc);
-      const float sc = (float)acc;
-      if (lane == 0 && (cnt < L || better(sc, (int)j, lv[L - 1], li[L - 1]))) {
-        int p = (cnt < L) ? cnt : L - 1;
-        while (p > 0 && better(sc, (int)j, lv[p - 1], li[p - 1])) {
-          lv[p] = lv[p - 1];
-          li[p] = li[p - 1];
-          --p;
+        for (int d = lane; d < D; d += 32) {
+          const double q = (double)yi[d];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(q, (double)yj[u][d], acc[u]);
         }
-        lv[p] = sc;
-        li[p] = (int)j;
-        if (cnt < L) ++cnt;
+      }
+      const double tot = warp_sum4(acc, lane);  // lane 8u holds the total of column u
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float sc = (float)__shfl_sync(0xffffffffu, tot, 8 * u);
+        const int64_t j = jj[u];
+        if (lane == 0 && j >= 0 && (cnt < L || better(sc, (int)j, lv[L - 1], li[L - 1]))) {
+          int p = (cnt < L) ? cnt : L - 1;
+          while (p > 0 && better(sc, (int)j, lv[p - 1], li[p - 1])) {
+            lv[p] = lv[p - 1];
+            li[p] = li[p - 1];
+            --p;
+          }
+          lv[p] = sc;
+          li[p] = (int)j;
+          if (cnt < L) ++cnt;
+        }
       }
     }
     if (lane == 0) {
