@@ -437,9 +437,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant
 //   F16 = true  (OSC_KNN_TCH): fp16 operands, kind::f16, K = 16 per MMA.  fp16 carries the same 11
 //     significant bits as tf32, and the entries of a unit row sit in its normal range (|x| <= 1; below
 //     2^-14 the absolute error is <= 2^-25), so the error bound is the same -- at half the operand
-//     bytes (the kernel is bound by L2 -> shared-memory traffic at N ~ 1e3) and twice the MMA rate
-//     (it is tensor-bound at N ~ 1e6).  A 128-byte swizzle row holds 64 halves instead of 32 floats;
-//     the stage layout in BYTES, the descriptors and the +32 B K-step are unchanged.
+//     bytes and twice the MMA rate.  That pays where the kernel is tensor-bound (N ~ 1e6: 2.19 s ->
+//     1.34 s at N=1M D=768); at N ~ 1e3 the top-k epilogue bounds it and the operand type hardly
+//     matters (14.8 -> 14.4 ms) -- see PACKED / EW below.  A 128-byte swizzle row holds 64 halves
+//     instead of 32 floats; the stage layout in BYTES, the descriptors and the +32 B K-step are unchanged.
 constexpr int TC2_HALF_BYTES = 128 * TC_BK * 4;                     // 128 rows x 32 floats
 template <bool ONEPASS>
 struct Tc2Cfg {
