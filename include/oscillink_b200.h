@@ -199,6 +199,17 @@ int osc_pcg_setup(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t m
                   const float* psi, const float* gates_loc, float* X_loc, float* Bv_loc,
                   void* stream);
 
+/* ------------------------------------------------------------------ chain prior (a6)
+ * Replaces build_path_laplacian (oscillink/core/graph.py:96-111) as called by add_chain
+ * (oscillink/core/lattice.py:129-149).  HOST function (every pointer is a host pointer): a chain is
+ * O(len) data, the N x N path Laplacian of the reference never exists.  Fills the arrays an osc_chain_t
+ * points at (upload them to the device): rows[n_rows] ascending, rowptr[n_rows+1], col/Wp/Ap[nnz]
+ * (columns ascending inside a row), slot[N].  weights: len-1 entries or NULL (all 1, lattice.py:129).
+ * OSC_ERR_INVALID for len < 2 or an index outside [0, N) (lattice.py:135-142). */
+int osc_chain_build_size(const int32_t* h_chain, int32_t len, int64_t N, int32_t* h_n_rows, int32_t* h_nnz);
+int osc_chain_build(const int32_t* h_chain, int32_t len, const float* h_weights, int64_t N, int32_t* h_rows,
+                    int32_t* h_rowptr, int32_t* h_col, float* h_Wp, float* h_Ap, int32_t* h_slot);
+
 /* R = Bv - Aop(X); P = R/(Mdiag+1e-12) (or R); partial rz.  X_all is the gathered x0. */
 int osc_pcg_residual0(const osc_pcg_dims_t* dims, const osc_graph_t* g, const osc_chain_t* chain,
                       const osc_params_t* prm, int32_t mode, float dt, int32_t jacobi,

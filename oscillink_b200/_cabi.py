@@ -60,6 +60,8 @@ PROTOTYPES = {
     "osc_device_info": (C.c_int, [C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]),
     "osc_normalize_rows": (C.c_int, [c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osc_normalize_rows_f16": (C.c_int, [c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p]),
+    "osc_chain_build_size": (C.c_int, [c_void_p, c_i32, c_i64, P(c_i32), P(c_i32)]),
+    "osc_chain_build": (C.c_int, [c_void_p, c_i32, c_void_p, c_i64] + [c_void_p] * 6),
     "osc_knn_candidates": (C.c_int, [c_void_p] * 6 + [c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32,
                                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "osc_knn_tc_supported": (C.c_int, [c_i64, c_i32, c_i32]),

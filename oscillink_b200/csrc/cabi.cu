@@ -1,8 +1,11 @@
 // extern "C" surface declared in include/oscillink_b200.h.  No exceptions cross this boundary:
 // every entry point returns a status code and records the failure text per host thread.
 #include <cstdio>
+#include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -277,6 +280,86 @@ int osc_graph_assemble(const int32_t* top_idx, const float* top_sim, int64_t bat
   OSC_REQUIRE(k >= 1 && batch <= 65535, "graph_assemble: bad k/batch");
   return launch_assemble(top_idx, top_sim, batch, N, k, row_cap, nbr, A, W, deg, sqrt_deg, nnz, scratch,
                          (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ chain prior (a6), host side
+// graph.py:101-111 / lattice.py:129-149 in sparse form.  A chain is O(len) data that the caller holds on
+// the host, so this is plain C++: max-merged symmetric path weights, CSR over the distinct chain nodes
+// (rows ascending, columns ascending inside a row), sdp_u = sqrt(max(rowsum_u, 1e-12)) accumulated in
+// fp32 in column order, Wp_uv = (Ap_uv * (1/sdp_u)) * (1/sdp_v) -- the rounding sequence of the
+// reference's normalized_laplacian (graph.py:87-92).
+static int chain_collect(const int32_t* h_chain, int32_t len, const float* h_weights, int64_t N,
+                         std::map<std::pair<int32_t, int32_t>, float>& ap) {
+  OSC_REQUIRE(h_chain != nullptr && len >= 2, "chain_build: chain must contain at least two indices");
+  for (int32_t t = 0; t < len; ++t)
+    OSC_REQUIRE(h_chain[t] >= 0 && (int64_t)h_chain[t] < N, "chain_build: chain indices out of bounds");
+  for (int32_t t = 0; t + 1 < len; ++t) {
+    const int32_t u = h_chain[t], v = h_chain[t + 1];
+    const float w = h_weights ? h_weights[t] : 1.0f;
+    float& a = ap[{u, v}];  // value-initialised to 0
+    if (w > a) a = w;
+    float& b = ap[{v, u}];
+    if (w > b) b = w;
+  }
+  return OSC_OK;
+}
+
+int osc_chain_build_size(const int32_t* h_chain, int32_t len, int64_t N, int32_t* h_n_rows, int32_t* h_nnz) {
+  std::map<std::pair<int32_t, int32_t>, float> ap;
+  const int rc = chain_collect(h_chain, len, nullptr, N, ap);
+  if (rc) return rc;
+  int32_t rows = 0, last = -1;
+  for (const auto& e : ap)
+    if (e.first.first != last) {
+      last = e.first.first;
+      ++rows;
+    }
+  if (h_n_rows) *h_n_rows = rows;
+  if (h_nnz) *h_nnz = (int32_t)ap.size();
+  return OSC_OK;
+}
+
+int osc_chain_build(const int32_t* h_chain, int32_t len, const float* h_weights, int64_t N, int32_t* h_rows,
+                    int32_t* h_rowptr, int32_t* h_col, float* h_Wp, float* h_Ap, int32_t* h_slot) {
+  OSC_REQUIRE(h_rows && h_rowptr && h_col && h_Wp && h_Ap && h_slot, "chain_build: NULL output");
+  std::map<std::pair<int32_t, int32_t>, float> ap;
+  const int rc = chain_collect(h_chain, len, h_weights, N, ap);
+  if (rc) return rc;
+  for (int64_t i = 0; i < N; ++i) h_slot[i] = -1;
+  std::vector<float> sdp;
+  int32_t n_rows = 0, nnz = 0, last = -1;
+  float d = 0.f;
+  h_rowptr[0] = 0;
+  for (const auto& e : ap) {  // ordered by (u, v)
+    const int32_t u = e.first.first;
+    if (u != last) {
+      if (last >= 0) {
+        sdp.push_back(sqrtf(fmaxf(d, 1e-12f)));
+        h_rowptr[n_rows] = nnz;
+      }
+      h_rows[n_rows] = u;
+      h_slot[u] = n_rows;
+      ++n_rows;
+      last = u;
+      d = 0.f;
+    }
+    d = d + e.second;  // fp32, column order
+    h_col[nnz] = e.first.second;
+    h_Ap[nnz] = e.second;
+    ++nnz;
+  }
+  sdp.push_back(sqrtf(fmaxf(d, 1e-12f)));
+  h_rowptr[n_rows] = nnz;
+  for (int32_t r = 0; r < n_rows; ++r) {
+    const float inv_u = 1.0f / sdp[r];
+    for (int32_t e = h_rowptr[r]; e < h_rowptr[r + 1]; ++e) {
+      // a neighbour that only appears as a column always has its own row (symmetry)
+      const float inv_v = 1.0f / sdp[h_slot[h_col[e]]];
+      const float t = h_Ap[e] * inv_u;
+      h_Wp[e] = t * inv_v;
+    }
+  }
+  return OSC_OK;
 }
 
 int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int32_t flags,

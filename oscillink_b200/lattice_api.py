@@ -368,47 +368,36 @@ class OscillinkLattice:
         self._log("clear_chain", {})
 
     def _make_chain(self, chain, weights) -> dict[str, Any]:
-        """graph.py:101-111 as a CSR over the distinct chain nodes: max-merged symmetric path
-        weights, then Wp_uv = (Ap_uv / sdp_u) / sdp_v with sdp = sqrt(max(rowsum, 1e-12))."""
-        if weights is None:
-            weights = [1.0] * (len(chain) - 1)
-        ap: dict[tuple[int, int], np.float32] = {}
-        for t in range(len(chain) - 1):
-            u, v = int(chain[t]), int(chain[t + 1])
-            w = _F32(weights[t])
-            ap[(u, v)] = max(ap.get((u, v), _F32(0)), w)
-            ap[(v, u)] = max(ap.get((v, u), _F32(0)), w)
-        rows = sorted({u for (u, _) in ap})
-        pos = {u: s for s, u in enumerate(rows)}
-        per_row: list[list[tuple[int, np.float32]]] = [[] for _ in rows]
-        for (u, v), w in sorted(ap.items()):
-            per_row[pos[u]].append((v, w))
-        sdp = {}
-        for u in rows:
-            d = _F32(0)
-            for _, w in per_row[pos[u]]:
-                d = _F32(d + w)
-            sdp[u] = _F32(np.sqrt(max(d, _F32(1e-12))))
-        rowptr, col, wp, apv = [0], [], [], []
-        wp_host = {}
-        for u in rows:
-            for v, w in per_row[pos[u]]:
-                # a neighbour that only appears as a column always has its own row (symmetry)
-                val = _F32(_F32(w * (_F32(1) / sdp[u])) * (_F32(1) / sdp[v]))
-                col.append(v)
-                wp.append(val)
-                apv.append(w)
-                wp_host[(u, v)] = val
-            rowptr.append(len(col))
-        slot = np.full(self.N, -1, dtype=np.int32)
-        slot[np.array(rows, dtype=np.int64)] = np.arange(len(rows), dtype=np.int32)
+        """graph.py:101-111 as a CSR over the distinct chain nodes (osc_chain_build, a host function of
+        the C ABI): max-merged symmetric path weights, then Wp_uv = (Ap_uv / sdp_u) / sdp_v with
+        sdp = sqrt(max(rowsum, 1e-12))."""
+        lib = _cabi.load()
+        ch = np.ascontiguousarray(np.asarray(chain, dtype=np.int64).astype(np.int32))
+        wts = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=_F32))
+        n_rows, nnz = C.c_int32(0), C.c_int32(0)
+        _cabi.check(lib.osc_chain_build_size(ch.ctypes.data, len(ch), self.N, C.byref(n_rows), C.byref(nnz)),
+                    "osc_chain_build_size")
+        rows = np.empty(n_rows.value, dtype=np.int32)
+        rowptr = np.empty(n_rows.value + 1, dtype=np.int32)
+        col = np.empty(nnz.value, dtype=np.int32)
+        wp = np.empty(nnz.value, dtype=_F32)
+        apv = np.empty(nnz.value, dtype=_F32)
+        slot = np.empty(self.N, dtype=np.int32)
+        _cabi.check(lib.osc_chain_build(ch.ctypes.data, len(ch), None if wts is None else wts.ctypes.data, self.N,
+                                        rows.ctypes.data, rowptr.ctypes.data, col.ctypes.data, wp.ctypes.data,
+                                        apv.ctypes.data, slot.ctypes.data), "osc_chain_build")
+        # host copies for chain_receipt / export_state: {(u, v): value}
+        ap, wp_host = {}, {}
+        for r, u in enumerate(rows.tolist()):
+            for e in range(int(rowptr[r]), int(rowptr[r + 1])):
+                ap[(u, int(col[e]))] = _F32(apv[e])
+                wp_host[(u, int(col[e]))] = _F32(wp[e])
         dev = self._dev
-        as_dev = lambda a, dt: torch.from_numpy(np.asarray(a, dtype=dt)).to(dev)  # noqa: E731
+        as_dev = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
         return {
-            "n_rows": len(rows), "nnz": len(col), "rows": as_dev(rows, np.int32),
-            "rowptr": as_dev(rowptr, np.int32), "col": as_dev(col, np.int32),
-            "Wp": as_dev(wp, _F32), "Ap": as_dev(apv, _F32), "slot": torch.from_numpy(slot).to(dev),
-            "ap_host": ap, "wp_host": wp_host,
+            "n_rows": int(n_rows.value), "nnz": int(nnz.value), "rows": as_dev(rows),
+            "rowptr": as_dev(rowptr), "col": as_dev(col), "Wp": as_dev(wp), "Ap": as_dev(apv),
+            "slot": as_dev(slot), "ap_host": ap, "wp_host": wp_host,
         }
 
     # ------------------------------------------------------------------ solves (K2 / K3)
