@@ -190,6 +190,9 @@ typedef struct osc_pcg_dims {
 
 /* fills dims->n_blocks and reports the workspace bytes osc_pcg_solve needs */
 int osc_pcg_plan(osc_pcg_dims_t* dims, size_t* h_ws_bytes);
+/* Largest ELL width k the SpMM kernels can launch for D columns (the graph chunk of a row block is staged
+ * in shared memory).  Graph loaders that adopt a caller-supplied adjacency (lattice.py:709-713) check it. */
+int osc_pcg_max_ell_width(int32_t D);
 
 /* x0 (lattice.py:751-758) and right-hand side (lattice.py:171,184 / :245):
  * X_loc = Y | U | (1-w)Y + wU ; Bv_loc = U + dt*(lamG*Y + lamQ*b*psi^T)  (settle)

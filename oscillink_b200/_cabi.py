@@ -80,6 +80,7 @@ PROTOTYPES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
     "osc_pcg_plan": (C.c_int, [P(PcgDims), P(c_size_t)]),
+    "osc_pcg_max_ell_width": (C.c_int, [c_i32]),
     "osc_pcg_setup": (C.c_int, [P(PcgDims), P(Params), c_i32, c_f32, c_i32, c_f32, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osc_pcg_residual0": (C.c_int, [P(PcgDims), P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32,

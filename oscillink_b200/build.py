@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libosc_b200.so")
-SOURCES = ["cabi.cu", "knn.cu", "knn_tc.cu", "graph.cu", "pcg.cu", "receipt.cu", "batched.cu", "bundle.cu"]
+SOURCES = ["cabi.cu", "knn.cu", "knn_tc.cu", "graph.cu", "pcg.cu", "receipt.cu", "batched.cu", "batched_ms.cu", "bundle.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -52,6 +52,7 @@ int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
                     int32_t*, float*, int64_t*, float*, cudaStream_t);
 int pcg_plan(osc_pcg_dims_t*, size_t*);
+int pcg_max_ell_width(int);
 int pcg_setup(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, float, const float*,
               const float*, const float*, const float*, float*, float*, cudaStream_t);
 int pcg_residual0(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
@@ -447,6 +448,7 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
 
 // ------------------------------------------------------------------ PCG
 int osc_pcg_plan(osc_pcg_dims_t* dims, size_t* h_ws_bytes) { return pcg_plan(dims, h_ws_bytes); }
+int osc_pcg_max_ell_width(int32_t D) { return D >= 1 ? pcg_max_ell_width(D) : 0; }
 
 int osc_pcg_setup(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
                   int32_t warm_start, float inertia, const float* Y_loc, const float* U_loc,

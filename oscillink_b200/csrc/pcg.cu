@@ -161,13 +161,15 @@ __device__ __forceinline__ const float* row_ptr(const VecView& v, int64_t j, int
 // gather loop has no dependent index load in front of every row fetch and can keep 8 row fetches
 // per thread in flight (the kernel is latency-bound on random 4*D-byte rows otherwise).
 // blockIdx.y selects the 256-column-group panel when D/VEC > 256.
+// The chunk is SPMM_RCH rows; very wide ELL rows (dense adjacencies adopted by from_state) shrink it so
+// that the staged chunk still fits in shared memory (`rch` argument).
 constexpr int SPMM_RCH = 32;
 
 template <int VEC, bool RES0>
 __global__ void __launch_bounds__(256)
 pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
                 VecView vv, float* __restrict__ out, float* __restrict__ Pout,
-                double* __restrict__ part) {
+                double* __restrict__ part, int rch) {
   extern __shared__ double sh[];
   const int CG = dm.D / VEC;
   const int nthr = blockDim.x * blockDim.y;
@@ -175,8 +177,8 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
   // staged per chunk: the ADDRESS of every neighbour row (resolved once per chunk, not per column
   // thread), its weight, the row degrees
   const float** s_nb = reinterpret_cast<const float**>(sh + (size_t)nthr * VEC);
-  float* s_w = reinterpret_cast<float*>(s_nb + SPMM_RCH * g.k);
-  int32_t* s_deg = reinterpret_cast<int32_t*>(s_w + SPMM_RCH * g.k);
+  float* s_w = reinterpret_cast<float*>(s_nb + (size_t)rch * g.k);
+  int32_t* s_deg = reinterpret_cast<int32_t*>(s_w + (size_t)rch * g.k);
   const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
   const int64_t r_beg = (int64_t)blockIdx.x * rpb;
   const int64_t r_end = min(dm.n_local, r_beg + rpb);
@@ -187,8 +189,8 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
   double acc[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-  for (int64_t c0 = r_beg; c0 < r_end; c0 += SPMM_RCH) {
-    const int rows = (int)min((int64_t)SPMM_RCH, r_end - c0);
+  for (int64_t c0 = r_beg; c0 < r_end; c0 += rch) {
+    const int rows = (int)min((int64_t)rch, r_end - c0);
     __syncthreads();  // the previous chunk's readers are done
     for (int e = tid; e < rows * g.k; e += nthr) {
       const int32_t j = g.nbr[c0 * g.k + e];
@@ -493,6 +495,28 @@ int pcg_setup(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float 
   return OSC_OK;
 }
 
+// dynamic shared memory of pcg_spmm_kernel: fp64 partials + one staged graph chunk of `rch` rows
+static constexpr size_t kSpmmSmemMax = 227 * 1024;
+static size_t spmm_smem_bytes(const dim3& blk, int vec, int k, int rch) {
+  return (size_t)blk.x * blk.y * vec * sizeof(double) + (size_t)rch * ((size_t)k * 12 + 4);
+}
+// rows per staged chunk: SPMM_RCH when that fits the 48 KB default, else the largest power of two that
+// does; ELL rows too wide even for one row per chunk use the opt-in limit.  0 = does not fit at all.
+static int spmm_chunk_rows(const dim3& blk, int vec, int k) {
+  for (int rch = SPMM_RCH; rch >= 1; rch >>= 1)
+    if (spmm_smem_bytes(blk, vec, k, rch) <= 48 * 1024) return rch;
+  return spmm_smem_bytes(blk, vec, k, 1) <= kSpmmSmemMax ? 1 : 0;
+}
+
+// largest ELL width the staged SpMM can launch for D columns (graph loaders check it up front)
+int pcg_max_ell_width(int D) {
+  int vec;
+  dim3 blk;
+  block_shape(D, vec, blk);
+  const size_t fixed = (size_t)blk.x * blk.y * vec * sizeof(double) + 4;
+  return (int)((kSpmmSmemMax - fixed) / 12);
+}
+
 static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
                        const osc_chain_t* chain, const osc_params_t* prm, int mode, float dt,
                        int jacobi, const float* gates, VecView vv, float* out, float* Pout,
@@ -505,16 +529,24 @@ static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
     if (vec == 4) return fail(OSC_ERR_INVALID, "pcg: vectors must be 16-byte aligned when D % 4 == 0");
   }
   Coef c = make_coef(prm, mode, dt, jacobi);
-  const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double) +
-                      (size_t)SPMM_RCH * (g->k * 12 + 4);
+  const int rch = spmm_chunk_rows(blk, vec, g->k);
+  if (rch == 0) return fail(OSC_ERR_UNSUPPORTED, "pcg: ELL width too large for the staged SpMM");
+  const size_t smem = spmm_smem_bytes(blk, vec, g->k, rch);
   const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
+#define OSC_SPMM_LAUNCH(R0)                                                                               \
+  OSC_VEC_DISPATCH(vec, {                                                                                 \
+    if (smem > 48 * 1024)                                                                                 \
+      OSC_CUDA(cudaFuncSetAttribute((const void*)pcg_spmm_kernel<VEC, R0>,                                \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmmSmemMax));    \
+    pcg_spmm_kernel<VEC, R0><<<grid, blk, smem, st>>>(to_dims(d), c, gview(g), cview(chain), gates, vv,  \
+                                                      out, Pout, part, rch);                              \
+  })
   if (res0) {
-    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, true><<<grid, blk, smem, st>>>(
-                              to_dims(d), c, gview(g), cview(chain), gates, vv, out, Pout, part);)
+    OSC_SPMM_LAUNCH(true)
   } else {
-    OSC_VEC_DISPATCH(vec, pcg_spmm_kernel<VEC, false><<<grid, blk, smem, st>>>(
-                              to_dims(d), c, gview(g), cview(chain), gates, vv, out, Pout, part);)
+    OSC_SPMM_LAUNCH(false)
   }
+#undef OSC_SPMM_LAUNCH
   OSC_LAUNCH_CHECK("pcg_spmm_kernel");
   return OSC_OK;
 }
@@ -647,11 +679,12 @@ int pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t
   if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
   if (h_iters) *h_iters = 0;
   if (h_res) *h_res = __builtin_nanf("");
-  if (g->N == 0 || max_iters < 1) return OSC_OK;
+  if (g->N == 0) return OSC_OK;
   Arena ar(workspace, ws_bytes);
   float* R = ar.take<float>((size_t)g->N * D);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
   if ((rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, R, st))) return rc;
+  if (max_iters < 1) return OSC_OK;  // no iteration: X = x0 (never uninitialised memory)
   return pcg_core(d, g, chain, prm, mode, dt, jacobi, tol, max_iters, gates, X, R, ar, h_iters, h_res, st);
 }
 

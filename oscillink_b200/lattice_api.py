@@ -283,8 +283,18 @@ class OscillinkLattice:
         if nbr.shape[1] == 0:
             nbr = np.full((self.N, 1), -1, dtype=np.int32)
             a = np.zeros((self.N, 1), dtype=_F32)
-        if np.any(nbr >= self.N):
+        nbr = np.asarray(nbr).astype(np.int64)
+        if np.any(nbr >= self.N) or np.any(nbr < -1):
             raise ValueError("A_ell column index out of bounds")
+        # the kernels read the first deg slots of a row: move the valid entries to the front, ascending
+        # (padding anywhere in the row and unsorted rows are accepted; duplicates are not)
+        key = np.where(nbr < 0, self.N, nbr)
+        order = np.argsort(key, axis=1, kind="stable")
+        nbr = np.take_along_axis(nbr, order, axis=1)
+        a = np.take_along_axis(np.asarray(a, dtype=_F32), order, axis=1)
+        if nbr.shape[1] > 1 and np.any((nbr[:, 1:] == nbr[:, :-1]) & (nbr[:, 1:] >= 0)):
+            raise ValueError("A_ell has duplicate column indices in a row")
+        self._check_ell_width(nbr.shape[1])
         a = np.where(nbr < 0, _F32(0), a).astype(_F32)
         d = a.sum(axis=1, dtype=_F32)
         sd = np.sqrt(np.maximum(d, _F32(1e-12))).astype(_F32)
@@ -300,6 +310,13 @@ class OscillinkLattice:
         self._sd = torch.from_numpy(sd).to(dev)
         self._invalidate_graph_views()
 
+    def _check_ell_width(self, width: int) -> None:
+        """A graph adopted from a caller (from_state / the A setter) may have rows far wider than a kNN
+        build produces; reject what the SpMM kernels cannot stage, before any device work."""
+        lim = int(self._lib.osc_pcg_max_ell_width(int(self.D)))
+        if width > lim:
+            raise ValueError(f"adjacency row degree {width} exceeds the supported ELL width {lim} for D={self.D}")
+
     def _load_dense_adjacency(self, dense: np.ndarray) -> None:
         """from_state support (lattice.py:709-713): adopt a user-supplied dense adjacency and
         recompute sqrt_deg / normalised weights the way graph.py:87-90 does."""
@@ -307,6 +324,7 @@ class OscillinkLattice:
             raise ValueError("A shape mismatch")
         mask = dense != 0
         width = max(1, int(mask.sum(axis=1).max()) if self.N else 1)
+        self._check_ell_width(width)
         nbr = np.full((self.N, width), -1, dtype=np.int32)
         a = np.zeros((self.N, width), dtype=_F32)
         for i in range(self.N):
@@ -329,19 +347,30 @@ class OscillinkLattice:
 
     # ------------------------------------------------------------------ public API
     def set_query(self, psi: np.ndarray, gates: np.ndarray | None = None) -> None:
-        self._hpsi = np.asarray(psi).astype(_F32).copy()
+        # the reference fails with a NumPy broadcasting ValueError at settle time when psi does not have
+        # D entries (lattice.py:184); here every kernel reads exactly D floats, so reject it up front
+        hpsi = np.asarray(psi).astype(_F32).reshape(-1).copy()
+        if hpsi.shape[0] != self.D:
+            raise ValueError(f"psi must have D={self.D} entries, got {hpsi.shape[0]}")
+        if gates is not None:
+            gates = self._check_gates(gates)
+        self._hpsi = hpsi
         self._dpsi = torch.from_numpy(self._hpsi).to(self._dev)
         if gates is not None:
-            if gates.shape[0] != self.N:
-                raise ValueError("gates length mismatch N")
-            self._hB = np.asarray(gates).astype(_F32).copy()
+            self._hB = gates
             self._dB = torch.from_numpy(self._hB).to(self._dev)
         self._invalidate_cache()
 
-    def set_gates(self, gates: np.ndarray) -> None:
-        if gates.shape[0] != self.N:
+    def _check_gates(self, gates) -> np.ndarray:
+        g = np.asarray(gates)
+        if g.ndim < 1 or g.shape[0] != self.N:
             raise ValueError("gates length mismatch N")
-        self._hB = np.asarray(gates).astype(_F32).copy()
+        if g.ndim != 1:
+            raise ValueError("gates must be a 1-D array of length N")
+        return g.astype(_F32).copy()
+
+    def set_gates(self, gates: np.ndarray) -> None:
+        self._hB = self._check_gates(gates)
         self._dB = torch.from_numpy(self._hB).to(self._dev)
         self._invalidate_cache()
 
@@ -894,7 +923,8 @@ class OscillinkLattice:
             nbr, a = self._ell_host()
             state["A_ell"] = {"nbr": nbr.tolist(), "val": a.tolist()}
         if include_chain and self._chain is not None:
-            state["chain_edges"] = sorted([int(u), int(v)] for (u, v) in self._chain["ap_host"] if u < v)
+            state["chain_edges"] = sorted([int(u), int(v)] for (u, v), w in self._chain["ap_host"].items()
+                                          if u < v and w > 0)  # lattice.py:606-611: only A_path > 0
             if self._chain_nodes is not None:
                 state["chain_nodes"] = list(self._chain_nodes)
         return state

@@ -92,6 +92,15 @@ def _validate(r: SettleRequest) -> None:
         raise ValueError("psi dimension mismatch")
     if r.gates is not None and r.gates.shape[0] != r.Y.shape[0]:
         raise ValueError("gates length mismatch N")
+    if r.kneighbors > 128:
+        raise ValueError("kneighbors must be <= 128")
+    if r.chain is not None:  # lattice.py:135-142, checked here so that one bad request cannot fail its group
+        if r.lamP < 0:
+            raise ValueError("lamP must be >= 0")
+        if any((c < 0 or c >= r.Y.shape[0]) for c in r.chain):
+            raise ValueError("chain indices out of bounds")
+        if len(r.chain) < 2:
+            raise ValueError("chain must contain at least two indices")
 
 
 # ----------------------------------------------------------------------------- CUDA backend
@@ -117,22 +126,25 @@ def cuda_backend(group: list[SettleRequest]) -> list[dict[str, Any]]:
 
         lib_ok = bool(_cabi.load().osc_batched_supported(n, d, min(r0.kneighbors, n - 1)))
     if not lib_ok:
-        out = []
+        out: list[Any] = []
         for r in group:  # shapes the slab kernel does not cover: the general single-lattice path
             t1 = time.time()
-            lat = OscillinkLattice(r.Y, kneighbors=r.kneighbors, row_cap_val=r.row_cap_val, lamG=r.lamG,
-                                   lamC=r.lamC, lamQ=r.lamQ, deterministic_k=True)
-            lat.set_query(r.psi, gates=r.gates)
-            if r.chain is not None:
-                lat.add_chain(r.chain, lamP=r.lamP)
-            st = lat.settle(dt=r.dt, max_iters=r.max_iters, tol=r.tol)
-            rec = None
-            if r.include_receipt:
-                lat.set_receipt_detail("light")
-                rec = lat.receipt()
-            out.append({"settle": dict(st), "receipt": rec, "state_sig": lat._signature(),
-                        "timings_ms": {"total_settle_ms": 1000.0 * (time.time() - t1)},
-                        "meta": {"N": n, "D": d, "batch_size": 1, "path": "single"}})
+            try:  # requests are independent here: a failing one becomes ITS result, not the group's
+                lat = OscillinkLattice(r.Y, kneighbors=r.kneighbors, row_cap_val=r.row_cap_val, lamG=r.lamG,
+                                       lamC=r.lamC, lamQ=r.lamQ, deterministic_k=True)
+                lat.set_query(r.psi, gates=r.gates)
+                if r.chain is not None:
+                    lat.add_chain(r.chain, lamP=r.lamP)
+                st = lat.settle(dt=r.dt, max_iters=r.max_iters, tol=r.tol)
+                rec = None
+                if r.include_receipt:
+                    lat.set_receipt_detail("light")
+                    rec = lat.receipt()
+                out.append({"settle": dict(st), "receipt": rec, "state_sig": lat._signature(),
+                            "timings_ms": {"total_settle_ms": 1000.0 * (time.time() - t1)},
+                            "meta": {"N": n, "D": d, "batch_size": 1, "path": "single"}})
+            except Exception as e:  # noqa: BLE001
+                out.append(e)
         return out
     B = len(group)
     Y = torch.from_numpy(np.stack([np.ascontiguousarray(r.Y, dtype=np.float32) for r in group])).pin_memory()
@@ -265,7 +277,11 @@ class SettleCoalescer:
             try:
                 results = self._backend(group)
                 for r, out in zip(group, results):
-                    r.future.set_result(out)
+                    # a backend may return an Exception in a request's slot (per-request failure)
+                    if isinstance(out, BaseException):
+                        r.future.set_exception(out)
+                    else:
+                        r.future.set_result(out)
             except BaseException as e:  # noqa: BLE001 -- the request threads must always be released
                 for r in group:
                     if not r.future.done():

@@ -565,12 +565,16 @@ class ShardedLattice:
     def set_query(self, psi, gates=None) -> None:
         import torch
 
-        self._dpsi = torch.as_tensor(np.asarray(psi, dtype=np.float32)).to(self._dev)
+        hpsi = np.asarray(psi, dtype=np.float32).reshape(-1)
+        if hpsi.shape[0] != self.D:
+            raise ValueError(f"psi must have D={self.D} entries, got {hpsi.shape[0]}")
         if gates is not None:
-            g = torch.as_tensor(np.asarray(gates, dtype=np.float32))
-            if g.shape[0] != self.N:
+            hg = np.asarray(gates, dtype=np.float32)
+            if hg.ndim != 1 or hg.shape[0] != self.N:
                 raise ValueError("gates length mismatch N")
-            self._dB_all = g.to(self._dev)
+        self._dpsi = torch.as_tensor(hpsi.copy()).to(self._dev)
+        if gates is not None:
+            self._dB_all = torch.as_tensor(hg.copy()).to(self._dev)
             self._dB_loc = self._dB_all[self.row0:self.row0 + self.n_local]
         self._Ustar = None
 

@@ -172,3 +172,92 @@ def test_settle_host_batch_pipelined_matches_resident():
     assert np.array_equal(got[:, 0], out["iters"].cpu().numpy().astype(np.float64))
     assert np.array_equal(got[:, 2], out["ustar_iters"].cpu().numpy().astype(np.float64))
     assert np.allclose(got[:, 4], out["deltaH"].cpu().numpy(), rtol=1e-12)
+
+
+# ------------------------------------------------------------------ multi-shift fast path (batched_ms.cu)
+@pytest.mark.parametrize("kw", [
+    dict(dt=1.0, max_iters=12, tol=1e-3, ustar_tol=1e-4),          # the serving call
+    dict(dt=0.5, max_iters=12, tol=1e-3, ustar_tol=1e-4),          # sigma = 2
+    dict(dt=1.0, max_iters=12, tol=1e-6, ustar_tol=1e-2),          # the stationary system stops FIRST
+    dict(dt=2.0, max_iters=2, tol=1e-9, ustar_tol=1e-4),           # settle capped by max_iters
+    dict(dt=1.0, max_iters=12, tol=1e-3, ustar_tol=1e-9, ustar_max_iters=3),  # U* capped by max_iters
+    dict(dt=1.0, max_iters=12, tol=1e-4, ustar_tol=1e-4),          # both stop at (about) the same iteration
+])
+def test_multishift_matches_two_solve_oracle(kw):
+    """settle + U* + deltaH from ONE multi-shift CG (first settle, uniform gates) against the oracle's two
+    separate PCG solves: same iteration counts, U / U* / deltaH within 1e-5."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    B, N, D, k = 3, 500, 40, 7
+    Y, psi = _inputs(B, N, D, seed0=200)
+    bl = BatchedLattices(Y, kneighbors=k, lamG=1.1, lamC=0.6, lamQ=3.5)
+    bl.set_query(psi)
+    out = bl.settle(receipt=True, keep_ustar=True, **kw)
+    torch.cuda.synchronize()
+    U, Us = bl.U.cpu().numpy(), bl.Ustar.cpu().numpy()
+    for b in range(B):
+        o = SparseLattice(Y[b], k=k, lamG=1.1, lamC=0.6, lamQ=3.5)
+        o.set_query(psi[b])
+        st = o.settle(dt=kw["dt"], max_iters=kw["max_iters"], tol=kw["tol"])
+        ous, it, res = o.stationary(tol=kw["ustar_tol"], max_iters=kw.get("ustar_max_iters", 64))
+        assert int(out["iters"][b].item()) == st["iters"]
+        assert int(out["ustar_iters"][b].item()) == it
+        assert rel(float(out["res"][b].item()), st["res"]) < 2e-3
+        assert rel(float(out["ustar_res"][b].item()), res) < 2e-3
+        assert np.linalg.norm(U[b] - o.U) / np.linalg.norm(o.U) < TOL
+        assert np.linalg.norm(Us[b] - ous) / np.linalg.norm(ous) < TOL
+        assert rel(float(out["deltaH"][b].item()), o.delta_h(ous)) < TOL
+
+
+@pytest.mark.parametrize("N,D,k", [(1200, 64, 8), (1210, 16, 12), (1280, 16, 16), (130, 8, 3), (1000, 24, 9)])
+def test_multishift_equals_two_solve_kernel(N, D, k, monkeypatch):
+    """The fast path and the two-solve kernel (OSC_BATCHED_MS=0) are the same recurrences up to fp32
+    rounding: every block size / ELL width variant, pad rows included."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    B = 2
+    Y, psi = _inputs(B, N, D, seed0=300)
+    outs = []
+    for ms in ("1", "0"):
+        monkeypatch.setenv("OSC_BATCHED_MS", ms)
+        bl = BatchedLattices(Y, kneighbors=k)
+        bl.set_query(psi)
+        out = bl.settle(receipt=True, keep_ustar=True)
+        torch.cuda.synchronize()
+        outs.append((bl.U.cpu().numpy(), bl.Ustar.cpu().numpy(), out["iters"].cpu().numpy(),
+                     out["ustar_iters"].cpu().numpy(), out["deltaH"].cpu().numpy(), out["res"].cpu().numpy()))
+    a, b = outs
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert np.linalg.norm(a[0] - b[0]) / np.linalg.norm(b[0]) < 2e-6
+    assert np.linalg.norm(a[1] - b[1]) / np.linalg.norm(b[1]) < 2e-6
+    assert np.allclose(a[4], b[4], rtol=1e-5)
+    assert np.allclose(a[5], b[5], rtol=2e-3)
+
+
+def test_multishift_uneven_slabs_forced_counts(monkeypatch):
+    """The fix pass of the fast path: slabs that stop early are re-run with forced (T_s, T_u)."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    B, N, D, k = 2, 320, 48, 6
+    Y, psi = _uneven_inputs(B, N, D)
+    res = {}
+    for ms in ("1", "0"):
+        monkeypatch.setenv("OSC_BATCHED_MS", ms)
+        bl = BatchedLattices(Y, kneighbors=k)
+        bl.set_query(psi)
+        out = bl.settle(receipt=True, keep_ustar=True)
+        torch.cuda.synchronize()
+        assert (out["unresolved"].cpu().numpy() & 2).all()
+        assert not (out["unresolved"].cpu().numpy() & 1).any()
+        res[ms] = (bl.U.cpu().numpy(), bl.Ustar.cpu().numpy(), out["iters"].cpu().numpy(),
+                   out["ustar_iters"].cpu().numpy(), out["deltaH"].cpu().numpy())
+    assert np.array_equal(res["1"][2], res["0"][2]) and np.array_equal(res["1"][3], res["0"][3])
+    for i in (0, 1):
+        assert np.linalg.norm(res["1"][i] - res["0"][i]) / np.linalg.norm(res["0"][i]) < 2e-6
+    assert np.allclose(res["1"][4], res["0"][4], rtol=1e-5)

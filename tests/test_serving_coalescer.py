@@ -97,3 +97,33 @@ def test_state_signature_matches_reference_value():
     pairs = np.stack([r.astype(np.int64), nbr[r, t].astype(np.int64)], axis=1)[:2048]
     sig = state_signature(c["psi"], np.ones(1200, np.float32), [1.0, 0.5, 4.0, 0.0], 8, True, pairs)
     assert sig == g["state_sig"]
+
+
+def test_a_failing_request_only_fails_its_own_future():
+    """A backend may put an Exception in one request's slot; the other requests of the group get results."""
+    def backend(group):
+        return [ValueError("bad request") if float(r.psi[0]) == 1.0 else {"ok": True} for r in group]
+
+    with SettleCoalescer(max_batch=8, max_wait_ms=200.0, backend=backend) as co:
+        Y = np.zeros((6, 4), np.float32)
+        futs = [co.submit(Y, np.full(4, float(i == 2), np.float32)) for i in range(5)]
+        for i, f in enumerate(futs):
+            if i == 2:
+                with pytest.raises(ValueError):
+                    f.result(timeout=10)
+            else:
+                assert f.result(timeout=10) == {"ok": True}
+
+
+def test_chain_and_kneighbors_are_validated_on_the_submitting_thread():
+    with SettleCoalescer(max_batch=2, max_wait_ms=1.0, backend=lambda g: [{} for _ in g]) as co:
+        Y = np.zeros((6, 4), np.float32)
+        with pytest.raises(ValueError):
+            co.submit(Y, np.zeros(4, np.float32), chain=[0, 9])
+        with pytest.raises(ValueError):
+            co.submit(Y, np.zeros(4, np.float32), chain=[1])
+        with pytest.raises(ValueError):
+            co.submit(Y, np.zeros(4, np.float32), chain=[0, 1], lamP=-1.0)
+        with pytest.raises(ValueError):
+            co.submit(Y, np.zeros(4, np.float32), kneighbors=129)
+        assert co.submit(Y, np.zeros(4, np.float32), chain=[0, 1]).result(timeout=10) == {}
