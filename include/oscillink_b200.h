@@ -283,6 +283,83 @@ int osc_pcg_solve_system(const osc_graph_t* g, const osc_chain_t* chain, const o
                          const float* gates, int32_t D, float* X, float* B, int32_t* h_iters,
                          float* h_res, void* workspace, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU solve (configs #4/#5)
+ * One process per GPU; these entry points take the rank's share of the lattice and an NCCL communicator
+ * and run the WHOLE solve (solver.py:19-37 across ranks): NCCL is called from inside the library on the
+ * caller's stream, the stop test (solver.py:29-31) is evaluated on the device after the all-reduce, and the
+ * host only polls its verdict.  NCCL is bound at run time (dlopen libnccl.so.2; the copy already loaded in
+ * the process is used), so the library itself has no NCCL link dependency.
+ *
+ * Partitions:
+ *   OSC_PART_ROWS     rank r owns rows [r*shard, min(N,(r+1)*shard)); graph arrays are the LOCAL rows with
+ *                     GLOBAL neighbour ids; Y/U/X/gates are local rows; D is the full width.  Per iteration:
+ *                     halo exchange of the search direction + all-reduce (SUM) of the 3*D column dots.
+ *       OSC_HALO_ALLGATHER  ncclAllGather of p in front of every SpMM.
+ *       OSC_HALO_PULL       every rank pulls the unique remote rows its graph references from the peers'
+ *                           blocks over NVLink peer memory (osc_peer_alloc / osc_peer_open mappings):
+ *                           P_block = [shard own rows | n_halo pulled rows][D]; halo_rows / halo_nbr come from
+ *                           osc_dist_halo_plan; a chain's `col` must then hold rows of the block as well
+ *                           (pass them through osc_dist_halo_plan's extra ids).
+ *   OSC_PART_COLUMNS  rank r owns ALL N rows of D columns (a slab of the lattice's width); the graph is the
+ *                     full graph; psi is the slab of psi.  No halo, no dot all-reduce: every reduction of
+ *                     solver.py:22-36 is per column; one 1-float MAX all-reduce per iteration. */
+#define OSC_PART_ROWS 0
+#define OSC_PART_COLUMNS 1
+#define OSC_HALO_ALLGATHER 0
+#define OSC_HALO_PULL 1
+
+typedef struct osc_dist {
+  void* nccl_comm; /* ncclComm_t (from osc_dist_comm_init, or any communicator of the same NCCL library) */
+  int32_t world, rank;
+  int32_t partition; /* OSC_PART_* */
+  int32_t halo;      /* OSC_HALO_* (rows partition) */
+  int64_t N;         /* global rows */
+  int64_t shard;     /* rows per rank = ceil(N / world) (rows partition) */
+  /* OSC_HALO_PULL only */
+  const float* const* d_peer_P; /* device table [world]: base of every rank's P_block (own entry included) */
+  float* P_block;               /* this rank's block [shard + n_halo][D] */
+  const int32_t* halo_rows;     /* [n_halo] ascending global ids of the remote rows this rank gathers */
+  const int32_t* halo_nbr;      /* [n_local][k] neighbour ids as rows of P_block (-1 padded) */
+  int64_t n_halo;
+} osc_dist_t;
+
+/* NCCL version of the bound library (OSC_ERR_UNSUPPORTED if NCCL cannot be loaded) */
+int osc_dist_nccl_version(int32_t* h_version);
+/* ncclGetUniqueId on rank 0 (128 bytes, to be sent to the other ranks by any means), ncclCommInitRank on the
+ * CURRENT device of every rank, ncclCommDestroy. */
+int osc_dist_unique_id(unsigned char* h_id128);
+int osc_dist_comm_init(const unsigned char* h_id128, int32_t world, int32_t rank, void** h_comm);
+int osc_dist_comm_destroy(void* comm);
+
+/* Halo plan of the rows partition for OSC_HALO_PULL.  nbr_loc: the local rows' neighbour ids [n_local][k]
+ * (global, -1 padded); extra_ids (optional): further global row ids the operator touches (a chain's `col`).
+ * Outputs: *h_n_halo = number of distinct remote rows; halo_rows[n_halo] ascending; nbr_out / extra_out =
+ * the same ids as rows of the block [shard own rows | halo rows] (local j -> j - row0, remote j -> shard +
+ * position in halo_rows).  Call with halo_rows == NULL (or too small a halo_cap) to query *h_n_halo only. */
+int osc_dist_halo_plan_workspace(int64_t N, size_t* h_bytes);
+int osc_dist_halo_plan(const int32_t* nbr_loc, int64_t n_local, int32_t k, const int32_t* extra_ids,
+                       int64_t n_extra, int64_t N, int64_t row0, int64_t shard, int32_t* halo_rows,
+                       int64_t halo_cap, int32_t* nbr_out, int32_t* extra_out, int64_t* h_n_halo,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+/* The halo exchange of OSC_HALO_PULL on its own (what osc_dist_pcg_solve runs in front of every SpMM): a
+ * stream-ordered cross-rank ordering point (1-float all-reduce on d_flag) + the pull of the halo rows into
+ * P_block.  Exported for measurement. */
+int osc_dist_halo_exchange(const osc_dist_t* dist, int32_t D, float* d_flag, void* stream);
+
+/* Whole distributed solve (replaces solver.py:19-36 + lattice.py:173-182 across ranks).  n_loc = g->N local
+ * rows, D = local columns.  Arguments as osc_pcg_solve; every rank receives the same *h_iters / *h_res. */
+int osc_dist_pcg_workspace(const osc_dist_t* dist, int64_t n_loc, int32_t D, size_t* h_bytes);
+int osc_dist_pcg_solve(const osc_dist_t* dist, const osc_graph_t* g, const osc_chain_t* chain,
+                       const osc_params_t* prm, int32_t mode, float dt, int32_t warm_start, float inertia,
+                       int32_t jacobi, double tol, int32_t max_iters, const float* Y, const float* U,
+                       const float* psi, const float* gates, int32_t D, float* X, int32_t* h_iters,
+                       float* h_res, void* workspace, size_t ws_bytes, void* stream);
+/* deltaH over the sharded state (receipts.py:21-25), summed over the ranks; workspace as above */
+int osc_dist_delta_h(const osc_dist_t* dist, const osc_graph_t* g, const osc_chain_t* chain,
+                     const osc_params_t* prm, const float* U, const float* Ustar, const float* gates,
+                     int32_t D, double* h_deltaH, void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ K4: receipts
  * deltaH = <U-U*, M (U-U*)>  (receipts.py:21-25).  workspace from osc_pcg_plan. */
 int osc_delta_h(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm,

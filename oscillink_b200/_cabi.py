@@ -52,6 +52,17 @@ class BatchedArgs(C.Structure):
                 ("max_iters_settle", c_i32), ("max_iters_ustar", c_i32), ("unresolved", c_void_p)]
 
 
+PART_ROWS, PART_COLUMNS = 0, 1
+HALO_ALLGATHER, HALO_PULL = 0, 1
+
+
+class Dist(C.Structure):
+    """osc_dist_t: one rank's view of a sharded lattice (include/oscillink_b200.h)."""
+    _fields_ = [("nccl_comm", c_void_p), ("world", c_i32), ("rank", c_i32), ("partition", c_i32),
+                ("halo", c_i32), ("N", c_i64), ("shard", c_i64), ("d_peer_P", c_void_p),
+                ("P_block", c_void_p), ("halo_rows", c_void_p), ("halo_nbr", c_void_p), ("n_halo", c_i64)]
+
+
 P = C.POINTER
 # name -> (restype, argtypes); every symbol declared in include/oscillink_b200.h
 PROTOTYPES = {
@@ -108,6 +119,20 @@ PROTOTYPES = {
     "osc_pcg_solve_system": (C.c_int, [P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32, c_f64, c_i32,
                                        c_void_p, c_i32, c_void_p, c_void_p, P(c_i32), P(c_f32), c_void_p,
                                        c_size_t, c_void_p]),
+    "osc_dist_nccl_version": (C.c_int, [P(c_i32)]),
+    "osc_dist_unique_id": (C.c_int, [c_void_p]),
+    "osc_dist_comm_init": (C.c_int, [c_void_p, c_i32, c_i32, P(c_void_p)]),
+    "osc_dist_comm_destroy": (C.c_int, [c_void_p]),
+    "osc_dist_halo_plan_workspace": (C.c_int, [c_i64, P(c_size_t)]),
+    "osc_dist_halo_plan": (C.c_int, [c_void_p, c_i64, c_i32, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p,
+                                     c_i64, c_void_p, c_void_p, P(c_i64), c_void_p, c_size_t, c_void_p]),
+    "osc_dist_halo_exchange": (C.c_int, [P(Dist), c_i32, c_void_p, c_void_p]),
+    "osc_dist_pcg_workspace": (C.c_int, [P(Dist), c_i64, c_i32, P(c_size_t)]),
+    "osc_dist_pcg_solve": (C.c_int, [P(Dist), P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32, c_f32, c_i32,
+                                     c_f64, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p,
+                                     P(c_i32), P(c_f32), c_void_p, c_size_t, c_void_p]),
+    "osc_dist_delta_h": (C.c_int, [P(Dist), P(Graph), P(Chain), P(Params), c_void_p, c_void_p, c_void_p, c_i32,
+                                   P(c_f64), c_void_p, c_size_t, c_void_p]),
     "osc_delta_h": (C.c_int, [P(Graph), P(Chain), P(Params), c_void_p, c_void_p, c_void_p, c_i32,
                               P(c_f64), c_void_p, c_size_t, c_void_p]),
     "osc_receipt_full": (C.c_int, [P(Graph), P(Params), c_void_p, c_void_p, c_void_p, c_void_p, c_i32,

@@ -264,11 +264,13 @@ class BatchedLattices:
 
 def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: int = 6, *,
                       chunk: int = 128, max_iters: int = 12, tol: float = 1e-3, receipt: bool = True,
-                      out_host: torch.Tensor | None = None, device: torch.device | None = None,
-                      **lattice_kw) -> torch.Tensor:
+                      out_host: torch.Tensor | None = None, U_host: torch.Tensor | None = None,
+                      device: torch.device | None = None, **lattice_kw) -> torch.Tensor:
     """End-to-end serving call on HOST buffers: for every lattice b of Y_host[B,N,D] (pinned fp32)
     run ctor + set_query(psi_host[b]) + settle + light receipt (cloud/app/main.py:916-939,1043,1061)
     and return a pinned [B,5] float64 host tensor {iters, res, ustar_iters, ustar_res, deltaH}.
+    U_host (optional, pinned [B,N,D] fp32) also receives the settled state of every lattice: its D2H copy
+    runs on a third stream, concurrently with the next chunk's H2D copy (PCIe is full duplex) and compute.
 
     The batch is cut into chunks; the H2D copy of chunk i+1 runs on a copy stream while chunk i is
     built and settled, so PCIe and the SMs work concurrently (two device staging buffers)."""
@@ -280,6 +282,7 @@ def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: 
     res_dev = torch.empty((B, 5), dtype=torch.float64, device=dev)
     comp = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(dev)
+    back = torch.cuda.Stream(dev) if U_host is not None else None
     bufY = [torch.empty((chunk, N, D), dtype=torch.float32, device=dev) for _ in range(2)]
     bufP = [torch.empty((chunk, D), dtype=torch.float32, device=dev) for _ in range(2)]
     copy.wait_stream(comp)
@@ -306,9 +309,15 @@ def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: 
             r[:, 2], r[:, 3], r[:, 4] = out["ustar_iters"], out["ustar_res"], out["deltaH"]
         free_ev[s] = torch.cuda.Event()
         free_ev[s].record(comp)
+        if back is not None:
+            back.wait_event(free_ev[s])
+            with torch.cuda.stream(back):
+                U_host[lo:hi].copy_(bl.U, non_blocking=True)
         pending.append((bl, out, lo, hi))
     out_host.copy_(res_dev, non_blocking=True)
     comp.synchronize()
+    if back is not None:
+        back.synchronize()
     # flagged lattices (pathological, see BatchedLattices.settle): redo with the global-test PCG.
     # bufY has been reused by then, so the chunk is fetched again from the host copy.
     for bl, out, lo, hi in pending:
@@ -321,4 +330,6 @@ def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: 
             if receipt:
                 r[:, 2], r[:, 3], r[:, 4] = out["ustar_iters"], out["ustar_res"], out["deltaH"]
             out_host[lo:hi].copy_(r)
+            if U_host is not None:
+                U_host[lo:hi].copy_(bl.U)
     return out_host

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libosc_b200.so")
-SOURCES = ["cabi.cu", "knn.cu", "knn_tc.cu", "graph.cu", "pcg.cu", "receipt.cu", "batched.cu", "batched_ms.cu", "bundle.cu"]
+SOURCES = ["cabi.cu", "knn.cu", "knn_tc.cu", "graph.cu", "pcg.cu", "dist.cu", "receipt.cu", "batched.cu", "batched_ms.cu", "bundle.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(_compile, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-lpthread", "-ldl", "-lrt"]  # NCCL: dlopen
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -707,6 +707,8 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   P.do_settle = a->do_settle; P.do_ustar = a->do_ustar; P.do_dh = a->do_deltaH;
   P.lamG = prm->lamG; P.lamC = prm->lamC; P.lamQ = prm->lamQ; P.dt = a->dt;
   P.tol_settle = a->tol_settle; P.tol_ustar = a->tol_ustar;
+  P.thr2_settle = batched_sq_threshold(a->tol_settle);
+  P.thr2_ustar = batched_sq_threshold(a->tol_ustar);
   P.max_iters_settle = a->max_iters_settle; P.max_iters_ustar = a->max_iters_ustar;
 
   const bool gates = a->gates != nullptr;
@@ -724,9 +726,13 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
     if (e && atoi(e) == 0) use_ms = false;
   }
   if (use_ms) {
-    int t_ms = 0;
+    int t_ms = 0, variant = 0;
     size_t smem_ms = 0;
-    BatchedFn f = batched_ms_pick(N, kq, &t_ms, &smem_ms);
+    {
+      const char* e = getenv("OSC_BATCHED_MS_VARIANT");  // dev-only: 1 = shared-memory-graph kernel
+      if (e) variant = atoi(e);
+    }
+    BatchedFn f = batched_ms_pick(N, kq, variant, &t_ms, &smem_ms);
     if (f != nullptr) {
       fn = f;
       threads = t_ms;

@@ -30,6 +30,7 @@ struct BatchedK {
   int use_ybuf;  // the kernel was given Np float4 of shared memory for the Y-slab prefetch buffer
   float lamG, lamC, lamQ, dt;
   double tol_settle, tol_ustar;
+  float thr2_settle, thr2_ustar;  // batched_sq_threshold(tol): the stop tests on squared norms (batched_ms.cu)
   int max_iters_settle, max_iters_ustar;
 };
 
@@ -233,6 +234,7 @@ __device__ __forceinline__ V4 apply_row(const float4* p_s, const ushort4* nbr_s,
 
 // kernel entry type of the slab kernels and the selector of the multi-shift variant (batched_ms.cu)
 typedef void (*BatchedFn)(BatchedK);
-BatchedFn batched_ms_pick(int64_t N, int kq, int* threads, size_t* smem_dyn);
+BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn);
+float batched_sq_threshold(double tol);
 
 }  // namespace osc

@@ -24,14 +24,53 @@
 // visits shared memory: two barriers and one STS per row and iteration instead of three and LDS + STS.
 //
 // State per row (registers): X_u, X_s, P, P_s, R, G -- six float4.  Two slabs in flight do not fit the
-// register file, so the kernel runs ONE CTA per SM with T threads x 2 rows.
+// register file, so the kernel runs ONE CTA per SM.  Two variants:
+//   GREG = true  (ELL width <= 8): T threads x 4 rows, ~190 registers per thread.  The thread's rows are
+//                the same for every slab and every pass, so their graph entries (byte offsets + weights,
+//                12 registers per row) are loaded ONCE per work item and stay in registers: the gather
+//                pass issues only the p loads (no index/weight loads in front of them, 22 % fewer
+//                shared-memory wavefronts) and has the registers to keep all of a row's loads in flight.
+//   GREG = false (wider rows): T threads x 2 rows, graph image in shared memory as in batched.cu.
+#include <cmath>
 #include <cstdlib>
 
 #include "batched_common.cuh"
 
 namespace osc {
 
-template <int TPT, int KQ, int T>
+// total over the nw per-warp partials of ONE component (lane & 3), unrolled: slots >= nw hold zeros
+template <int NW>
+__device__ __forceinline__ float block_total_cu(const float4* red, int lane) {
+  const float* rf = reinterpret_cast<const float*>(red);
+  constexpr int L = (NW * 4 + 31) / 32;
+  float v[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) v[i] = rf[lane + 32 * i];
+  float t = v[0];
+#pragma unroll
+  for (int i = 1; i < L; ++i) t += v[i];
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t;
+}
+
+// sum_t W_t v[nbr_t] for one row whose graph entries (byte offsets, weights) sit in registers
+template <int KQ>
+__device__ __forceinline__ V4 gather_regs(const float4* src, const ushort4 (&j)[KQ], const float4 (&w)[KQ]) {
+  V4 acc = v4_zero();
+  const char* pb = reinterpret_cast<const char*>(src);
+#pragma unroll
+  for (int c = 0; c < KQ; ++c) {
+    acc = v4_fma_s(w[c].x, lds_v4(pb + j[c].x), acc);
+    acc = v4_fma_s(w[c].y, lds_v4(pb + j[c].y), acc);
+    acc = v4_fma_s(w[c].z, lds_v4(pb + j[c].z), acc);
+    acc = v4_fma_s(w[c].w, lds_v4(pb + j[c].w), acc);
+  }
+  return acc;
+}
+
+template <int TPT, int KQ, int T, bool GREG>
 __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int Np = T * TPT;
@@ -39,23 +78,32 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   // both gather sources are STATIC shared memory: a gather is LDS.128 [u16 offset + constant]
   __shared__ __align__(16) float4 r_static[Np];  // r_k (the gathered vector)
   __shared__ __align__(16) float4 y_static[Np];  // the slab's 4 columns of Y, prefetched with cp.async
+  __shared__ __align__(16) float4 redA[RED_F4];  // p.Ap / deltaH partials (slots >= nw stay zero)
+  __shared__ __align__(16) float4 redB[RED_F4];  // r.r partials
   const int N = P.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float4* w_s = reinterpret_cast<float4*>(smem_raw);              // [KQ][Np]
-  float4* redA = w_s + (size_t)Np * KQ;                           // p.Ap / deltaH partials
-  float4* redB = redA + RED_F4;                                   // r.r partials
-  ushort4* nbr_s = reinterpret_cast<ushort4*>(redB + RED_F4);     // [KQ][Np]
-  for (int e = tid; e < Np * KQ; e += T) {
-    w_s[e] = f4_zero();
-    nbr_s[e] = make_ushort4(0, 0, 0, 0);
+  float4* w_s = reinterpret_cast<float4*>(smem_raw);                  // [KQ][Np]   (GREG: unused)
+  ushort4* nbr_s = reinterpret_cast<ushort4*>(w_s + (size_t)Np * KQ);  // [KQ][Np]
+  if (!GREG) {
+    for (int e = tid; e < Np * KQ; e += T) {
+      w_s[e] = f4_zero();
+      nbr_s[e] = make_ushort4(0, 0, 0, 0);
+    }
   }
   for (int e = tid; e < Np; e += T) {
     r_static[e] = f4_zero();
     y_static[e] = f4_zero();
   }
-  bool act[TPT];
+  if (tid < RED_F4) {
+    redA[tid] = f4_zero();
+    redB[tid] = f4_zero();
+  }
+  bool act[TPT], wact[TPT];
 #pragma unroll
-  for (int m = 0; m < TPT; ++m) act[m] = (tid + T * m) < N;
+  for (int m = 0; m < TPT; ++m) {
+    act[m] = (tid + T * m) < N;
+    wact[m] = (warp * 32 + T * m) < N;  // warp-uniform: some lane of this warp owns a real row
+  }
 
   const bool list_mode = P.fix_list != nullptr;
   const int64_t n_work = list_mode ? (int64_t)(*P.fix_count) : P.n_work;
@@ -76,6 +124,10 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   const float sigma = __fdiv_rn(1.0f, P.dt);
   const V4 IM = v4_bc(im);
 
+  // graph entries of this thread's rows (GREG): byte offsets into the gathered vector + weights
+  ushort4 jj[GREG ? TPT : 1][KQ];
+  float4 ww[GREG ? TPT : 1][KQ];
+
   for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
     int64_t b;
     int s0, s1, Fs = 0, Fu = 0;
@@ -87,8 +139,19 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
       s0 = (int)(wk - b * P.cpl) * P.CH;
       s1 = min(s0 + P.CH, P.G);
     }
-    __syncthreads();  // readers of the previous graph image are done
-    {
+    if constexpr (GREG) {
+      const ushort4* src_n = reinterpret_cast<const ushort4*>(P.pk_nbr) + b * N * KQ;
+      const float4* src_w = reinterpret_cast<const float4*>(P.pk_w) + b * N * KQ;
+#pragma unroll
+      for (int m = 0; m < TPT; ++m) {
+#pragma unroll
+        for (int c = 0; c < KQ; ++c) {
+          jj[m][c] = act[m] ? __ldg(src_n + c * N + tid + T * m) : make_ushort4(0, 0, 0, 0);
+          ww[m][c] = act[m] ? __ldg(src_w + c * N + tid + T * m) : f4_zero();
+        }
+      }
+    } else {
+      __syncthreads();  // readers of the previous graph image are done
       const uint4* src_w = reinterpret_cast<const uint4*>(P.pk_w) + b * N * KQ;
       uint4* dst_w = reinterpret_cast<uint4*>(w_s);
       const uint2* src_n = reinterpret_cast<const uint2*>(P.pk_nbr) + b * N * KQ;
@@ -110,7 +173,7 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
       if (!y_ahead) y_fetch(b, s);
       cp_async_wait_all();
       y_ahead = false;
-      __syncthreads();  // Y slab + graph image visible; the previous slab's readers of r_static / red are done
+      __syncthreads();  // Y slab (+ graph image) visible; the previous slab's readers of r_static / red are done
       auto y_next = [&]() {  // issued once this slab has read Y for the last time
         if (s + 1 < s1) {
           y_fetch(b, s + 1);
@@ -129,27 +192,31 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
 #pragma unroll
       for (int m = 0; m < TPT; ++m) {
         const int row = tid + T * m;
-        const float4 y = y_static[row];
-        const V4 g0 = gather_row<KQ>(y_static, nbr_s, w_s, row, Np, KQ);
-        // lattice.py:184,256 (same rounding order); pad rows carry zeros
-        const float4 rhs = act[m] ? make_float4(__fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, psi4.x)),
-                                                __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, psi4.y)),
-                                                __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, psi4.z)),
-                                                __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, psi4.w)))
-                                  : f4_zero();
-        const V4 yv = to_v4(y);
-        Xu[m] = yv;
-        Xs[m] = yv;
-        R[m] = v4_sub(to_v4(rhs), combine_row(yv, g0, diag, noffc));
-        Pv[m] = v4_mul(IM, R[m]);
-        Ps[m] = R[m];
-        G[m] = v4_zero();
-        part = v4_fma(R[m], R[m], part);
-        sts_v4(r_static + row, R[m]);
+        Xu[m] = Xs[m] = Pv[m] = Ps[m] = R[m] = G[m] = v4_zero();
+        if (wact[m]) {
+          const float4 y = y_static[row];
+          const V4 g0 = GREG ? gather_regs<KQ>(y_static, jj[GREG ? m : 0], ww[GREG ? m : 0])
+                             : gather_row<KQ>(y_static, nbr_s, w_s, row, Np, KQ);
+          // lattice.py:184,256 (same rounding order); pad rows carry zeros
+          const float4 rhs = act[m]
+                                 ? make_float4(__fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, psi4.x)),
+                                               __fadd_rn(__fmul_rn(P.lamG, y.y), __fmul_rn(P.lamQ, psi4.y)),
+                                               __fadd_rn(__fmul_rn(P.lamG, y.z), __fmul_rn(P.lamQ, psi4.z)),
+                                               __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, psi4.w)))
+                                 : f4_zero();
+          const V4 yv = to_v4(y);
+          Xu[m] = yv;
+          Xs[m] = yv;
+          R[m] = v4_sub(to_v4(rhs), combine_row(yv, g0, diag, noffc));
+          Pv[m] = v4_mul(IM, R[m]);
+          Ps[m] = R[m];
+          part = v4_fma(R[m], R[m], part);
+          sts_v4(r_static + row, R[m]);
+        }
       }
       warp_reduce4(to_f4(part), redB + warp, lane);
       __syncthreads();  // r0 visible, r0.r0 partials visible
-      float rr = block_total_c(redB, nw, lane);  // column lane & 3
+      float rr = block_total_cu<nw>(redB, lane);  // column lane & 3
       float rz = rr * im;
       // per-column shift state (lane's column)
       float zeta = 1.f, zeta_p = 1.f, a_prev = 1.f, b_prev = 0.f, beta = 0.f;
@@ -164,19 +231,24 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
         part = v4_zero();
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
-          const int row = tid + T * m;
-          const V4 g = gather_row<KQ>(r_static, nbr_s, w_s, row, Np, KQ);
-          G[m] = v4_fma(IM, g, v4_mul(BETA, G[m]));
-          part = v4_fma(Pv[m], combine_row(Pv[m], G[m], diag, noffc), part);
+          if (wact[m]) {
+            const V4 g = GREG ? gather_regs<KQ>(r_static, jj[GREG ? m : 0], ww[GREG ? m : 0])
+                              : gather_row<KQ>(r_static, nbr_s, w_s, tid + T * m, Np, KQ);
+            G[m] = v4_fma(IM, g, v4_mul(BETA, G[m]));
+            part = v4_fma(Pv[m], combine_row(Pv[m], G[m], diag, noffc), part);
+          }
         }
         warp_reduce4(to_f4(part), redA + warp, lane);
         __syncthreads();  // B1: every gather of r_k is done
-        const float pap = block_total_c(redA, nw, lane);
-        const float alpha = __fdiv_rn(rz, pap + 1e-18f);  // solver.py:23
-        const float a = alpha * im;                        // plain-CG step length
+        const float pap = block_total_cu<nw>(redA, lane);
+        // solver.py:23.  The step lengths of the shift recurrences use the fast division: 2 ulp on alpha
+        // moves the iterates by ~1e-7 relative, far inside the 1e-5 parity bound, and is not on any knife
+        // edge (the stop tests below compare reduced norms, not quotients)
+        const float alpha = __fdividef(rz, pap + 1e-18f);
+        const float a = alpha * im;  // plain-CG step length
         const float den = a * b_prev * (zeta_p - zeta) + zeta_p * a_prev * (1.0f + sigma * a);
-        const float zn = den != 0.f ? __fdiv_rn(zeta * zeta_p * a_prev, den) : zeta;
-        const float ratio = zeta != 0.f ? __fdiv_rn(zn, zeta) : 0.f;
+        const float zn = den != 0.f ? __fdividef(zeta * zeta_p * a_prev, den) : zeta;
+        const float ratio = zeta != 0.f ? __fdividef(zn, zeta) : 0.f;
         const float4 al4 = bcast4(alpha);
         const V4 AL = to_v4(al4);
         const V4 NAL = to_v4(make_float4(-al4.x, -al4.y, -al4.z, -al4.w));
@@ -186,31 +258,33 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
         part = v4_zero();
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
-          const V4 ap = combine_row(Pv[m], G[m], diag, noffc);
-          Xu[m] = v4_fma(Pv[m], AU, Xu[m]);
-          Xs[m] = v4_fma(Ps[m], AS, Xs[m]);
-          R[m] = v4_fma(ap, NAL, R[m]);
-          part = v4_fma(R[m], R[m], part);
-          sts_v4(r_static + tid + T * m, R[m]);
+          if (wact[m]) {
+            const V4 ap = combine_row(Pv[m], G[m], diag, noffc);
+            Xu[m] = v4_fma(Pv[m], AU, Xu[m]);
+            Xs[m] = v4_fma(Ps[m], AS, Xs[m]);
+            R[m] = v4_fma(ap, NAL, R[m]);
+            part = v4_fma(R[m], R[m], part);
+            sts_v4(r_static + tid + T * m, R[m]);
+          }
         }
         warp_reduce4(to_f4(part), redB + warp, lane);
         __syncthreads();  // B2: r_{k+1} visible, r.r partials visible
-        const float rr_new = block_total_c(redB, nw, lane);
+        const float rr_new = block_total_cu<nw>(redB, lane);
         const float rzn = rr_new * im;
-        beta = __fdiv_rn(rzn, rz + 1e-18f);  // solver.py:34
+        beta = __fdividef(rzn, rz + 1e-18f);  // solver.py:34
         const float bs = beta * ratio * ratio;
-        // stop tests (solver.py:29-31): stationary on ||r||, settle on ||dt zeta r||, max over the slab's columns
+        // stop tests (solver.py:29-31): stationary on ||r||, settle on ||dt zeta r||, max over the slab's
+        // columns.  thr2_* is the largest fp32 x with (double)sqrtf(x) <= tol, so `m <= thr2` is exactly the
+        // reference's `float32 norm <= tol` without a square root or an fp64 compare on the critical path.
         const float zs = P.dt * zn;
         float mu = rr_new, ms = zs * zs * rr_new;
         mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 1));
-        mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 2));
         ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 1));
+        mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 2));
         ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
         // identical in every thread (same summation order) -> uniform branches
-        const bool stop_s = !fs && (Fs > 0 ? (k >= Fs)
-                                           : ((double)__fsqrt_rn(ms) <= P.tol_settle || k >= P.max_iters_settle));
-        const bool stop_u = !fu && (Fu > 0 ? (k >= Fu)
-                                           : ((double)__fsqrt_rn(mu) <= P.tol_ustar || k >= P.max_iters_ustar));
+        const bool stop_s = !fs && (Fs > 0 ? (k >= Fs) : (ms <= P.thr2_settle || k >= P.max_iters_settle));
+        const bool stop_u = !fu && (Fu > 0 ? (k >= Fu) : (mu <= P.thr2_ustar || k >= P.max_iters_ustar));
         if (stop_s) {
           // U+ out; M U+ = RHS + (Y - U+)/dt - zeta r  (the settle system's own residual is dt zeta r):
           // the dead p^s registers take t1 = (Y - U+)/dt - zeta r for the deltaH identity
@@ -288,38 +362,88 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
 }
 
 // ================================================================= host side
-// T threads x 2 rows; the smallest block that covers N keeps the pad rows (gathered like real ones) few
-static int ms_threads(int64_t N) {
-  static const int ts[] = {128, 256, 384, 512, 608, 640};
-  for (int t : ts)
-    if (2 * (int64_t)t >= N) return t;
-  return 0;
+// largest fp32 x with (double)sqrtf(x) <= tol (sqrtf is correctly rounded, like __fsqrt_rn): m <= x is the
+// reference's `float32 norm <= tol` (solver.py:29-31) evaluated on the squared norm
+float batched_sq_threshold(double tol) {
+  if (!(tol >= 0.0)) return -1.0f;  // negative / NaN tolerance: never satisfied
+  if (tol > 1.8e19) return INFINITY;
+  float x = (float)(tol * tol);
+  while (x > 0.f && (double)sqrtf(x) > tol) x = nextafterf(x, 0.f);
+  while ((double)sqrtf(nextafterf(x, INFINITY)) <= tol) x = nextafterf(x, INFINITY);
+  return x;
 }
 
-template <int T>
+template <int TPT, int T, bool GREG>
 static BatchedFn ms_pick_kq(int kq) {
-  switch (kq) {
-    case 1: return batched_ms_kernel<2, 1, T>;
-    case 2: return batched_ms_kernel<2, 2, T>;
-    case 3: return batched_ms_kernel<2, 3, T>;
-    default: return batched_ms_kernel<2, 4, T>;
+  if constexpr (GREG) {
+    return kq == 1 ? batched_ms_kernel<TPT, 1, T, true> : batched_ms_kernel<TPT, 2, T, true>;
+  } else {
+    switch (kq) {
+      case 1: return batched_ms_kernel<TPT, 1, T, false>;
+      case 2: return batched_ms_kernel<TPT, 2, T, false>;
+      case 3: return batched_ms_kernel<TPT, 3, T, false>;
+      default: return batched_ms_kernel<TPT, 4, T, false>;
+    }
   }
 }
 
+// smallest block (multiple of 32 threads, at most TMAX) whose T x TPT rows cover N
+template <int TPT, bool GREG, int TMAX>
+static BatchedFn ms_pick_t(int64_t N, int kq, int* threads) {
+  const int64_t t = ((N + TPT - 1) / TPT + 31) / 32 * 32;
+  if (t > TMAX) return nullptr;
+  *threads = (int)t;
+#define OSC_MS_CASE(TT) \
+  case TT:              \
+    if constexpr (TT <= TMAX) return ms_pick_kq<TPT, TT, GREG>(kq); else return nullptr;
+  switch ((int)t) {
+    OSC_MS_CASE(32) OSC_MS_CASE(64) OSC_MS_CASE(96) OSC_MS_CASE(128) OSC_MS_CASE(160) OSC_MS_CASE(192)
+    OSC_MS_CASE(224) OSC_MS_CASE(256) OSC_MS_CASE(288) OSC_MS_CASE(320)
+    default: return nullptr;
+  }
+#undef OSC_MS_CASE
+}
+
 // The multi-shift kernel that serves (N, kq), its block size and dynamic shared memory; nullptr if none.
-BatchedFn batched_ms_pick(int64_t N, int kq, int* threads, size_t* smem_dyn) {
-  const int t = ms_threads(N);
-  if (t == 0 || kq < 1 || kq > 4) return nullptr;
-  const size_t Np = (size_t)t * 2;
+// variant (dev A/B): 0 = auto, 1 = T x 2 rows + shared-memory graph, 2 = T x 4 rows + shared-memory graph,
+// 3 = T x 5 rows + graph in registers
+BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn) {
+  if (kq < 1 || kq > 4 || N < 1) return nullptr;
+  BatchedFn f = nullptr;
+  // measured on B200 (B = 1440, N = 1200, k = 8): T x 2 rows 16.95 ms, T x 4 rows 16.68 ms, T x 5 rows with the
+  // graph in registers 16.14 ms (the two-solve kernel: 21.2 ms)
+  if (variant == 0) variant = kq <= 2 ? 3 : 2;
+  if (variant == 3 && kq <= 2) {
+    f = ms_pick_t<5, true, 256>(N, kq, threads);
+    if (f != nullptr) {
+      *smem_dyn = 0;
+      return f;
+    }
+  }
+  if (variant >= 2) {
+    f = ms_pick_t<4, false, 320>(N, kq, threads);
+    if (f != nullptr) {
+      *smem_dyn = (size_t)*threads * 4 * kq * (16 + 8);
+      return f;
+    }
+  }
+  static const int ts[] = {128, 256, 384, 512, 608, 640};
+  int t = 0;
+  for (int v : ts)
+    if (2 * (int64_t)v >= N) {
+      t = v;
+      break;
+    }
+  if (t == 0) return nullptr;
   *threads = t;
-  *smem_dyn = Np * kq * (16 + 8) + 2 * RED_F4 * 16;
+  *smem_dyn = (size_t)t * 2 * kq * (16 + 8);
   switch (t) {
-    case 128: return ms_pick_kq<128>(kq);
-    case 256: return ms_pick_kq<256>(kq);
-    case 384: return ms_pick_kq<384>(kq);
-    case 512: return ms_pick_kq<512>(kq);
-    case 608: return ms_pick_kq<608>(kq);
-    default: return ms_pick_kq<640>(kq);
+    case 128: return ms_pick_kq<2, 128, false>(kq);
+    case 256: return ms_pick_kq<2, 256, false>(kq);
+    case 384: return ms_pick_kq<2, 384, false>(kq);
+    case 512: return ms_pick_kq<2, 512, false>(kq);
+    case 608: return ms_pick_kq<2, 608, false>(kq);
+    default: return ms_pick_kq<2, 640, false>(kq);
   }
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pcg.cuh"
 
 namespace osc {
 
@@ -51,32 +52,6 @@ int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_
                    const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t);
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
                     int32_t*, float*, int64_t*, float*, cudaStream_t);
-int pcg_plan(osc_pcg_dims_t*, size_t*);
-int pcg_max_ell_width(int);
-int pcg_setup(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, float, const float*,
-              const float*, const float*, const float*, float*, float*, cudaStream_t);
-int pcg_residual0(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
-                  int, float, int, const float*, const float*, float*, float*, double*, cudaStream_t);
-int pcg_spmm_dot(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
-                 int, float, const float*, const float*, float*, double*, cudaStream_t);
-int pcg_residual0_p2p(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
-                      int, float, int, const float*, const float* const*, int64_t, float*, float*, double*,
-                      cudaStream_t);
-int pcg_spmm_dot_p2p(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
-                     int, float, const float*, const float* const*, int64_t, float*, double*, cudaStream_t);
-int pcg_reduce(const double*, int, int, float*, float*, double*, cudaStream_t);
-int pcg_update(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, const float*, const float*,
-               const float*, const float*, const float*, float*, float*, double*, double*,
-               cudaStream_t);
-int pcg_pupdate(const osc_pcg_dims_t*, const osc_params_t*, int, float, int, const float*,
-                const float*, const float*, const float*, float*, cudaStream_t);
-int pcg_solve(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, int, float, int, float, int,
-              double, int, const float*, const float*, const float*, const float*, int, float*, int*,
-              float*, void*, size_t, cudaStream_t);
-int pcg_solve_system(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, int, float, int, double,
-                     int, const float*, int, float*, float*, int*, float*, void*, size_t, cudaStream_t);
-int delta_h(const osc_graph_t*, const osc_chain_t*, const osc_params_t*, const float*, const float*,
-            const float*, int, double*, void*, size_t, cudaStream_t);
 int launch_receipt_full(const osc_graph_t*, const osc_params_t*, const float*, const float*,
                         const float*, const float*, int, float, float*, float*, float*, int32_t*,
                         float*, float*, float*, float*, cudaStream_t);
@@ -84,6 +59,20 @@ int launch_row_align(const float*, const float*, int64_t, int, float*, cudaStrea
 int launch_pair_d2(const float*, const float*, const int32_t*, int64_t, int, float*, cudaStream_t);
 size_t mmr_workspace(int64_t N);
 int launch_mmr(const float*, const float*, int64_t, int, int, int32_t*, void*, size_t, cudaStream_t);
+int dist_nccl_version(int*);
+int dist_unique_id(unsigned char*);
+int dist_comm_init(const unsigned char*, int, int, void**);
+int dist_comm_destroy(void*);
+int dist_halo_plan_workspace(int64_t, size_t*);
+int dist_halo_plan(const int32_t*, int64_t, int, const int32_t*, int64_t, int64_t, int64_t, int64_t, int32_t*,
+                   int64_t, int32_t*, int32_t*, int64_t*, void*, size_t, cudaStream_t);
+int dist_pcg_workspace(const osc_dist_t*, int64_t, int, size_t*);
+int dist_halo_exchange(const osc_dist_t*, int, float*, cudaStream_t);
+int dist_pcg_solve(const osc_dist_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*, int, float,
+                   int, float, int, double, int, const float*, const float*, const float*, const float*, int,
+                   float*, int*, float*, void*, size_t, cudaStream_t);
+int dist_delta_h(const osc_dist_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*, const float*,
+                 const float*, const float*, int, double*, void*, size_t, cudaStream_t);
 int batched_supported(int64_t, int, int);
 int batched_workspace(int64_t, int64_t, int, size_t*);
 int batched_settle(const osc_graph_t*, const osc_params_t*, const osc_batched_args_t*, void*, size_t,
@@ -628,6 +617,55 @@ int osc_mmr_select(const float* Yn, const float* score, int64_t N, int32_t D, in
                    void* workspace, size_t ws_bytes, void* stream) {
   OSC_REQUIRE(Yn && score && chosen && D >= 1, "mmr_select: bad argument");
   return launch_mmr(Yn, score, N, D, k, chosen, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int osc_dist_nccl_version(int32_t* h_version) {
+  OSC_REQUIRE(h_version != nullptr, "osc_dist_nccl_version: NULL argument");
+  int v = 0;
+  const int rc = dist_nccl_version(&v);
+  *h_version = v;
+  return rc;
+}
+int osc_dist_unique_id(unsigned char* h_id128) {
+  OSC_REQUIRE(h_id128 != nullptr, "osc_dist_unique_id: NULL argument");
+  return dist_unique_id(h_id128);
+}
+int osc_dist_comm_init(const unsigned char* h_id128, int32_t world, int32_t rank, void** h_comm) {
+  OSC_REQUIRE(h_id128 != nullptr && h_comm != nullptr && world >= 1 && rank >= 0 && rank < world,
+              "osc_dist_comm_init: bad argument");
+  return dist_comm_init(h_id128, world, rank, h_comm);
+}
+int osc_dist_comm_destroy(void* comm) { return dist_comm_destroy(comm); }
+int osc_dist_halo_plan_workspace(int64_t N, size_t* h_bytes) {
+  OSC_REQUIRE(h_bytes != nullptr && N >= 0, "osc_dist_halo_plan_workspace: bad argument");
+  return dist_halo_plan_workspace(N, h_bytes);
+}
+int osc_dist_halo_plan(const int32_t* nbr_loc, int64_t n_local, int32_t k, const int32_t* extra_ids,
+                       int64_t n_extra, int64_t N, int64_t row0, int64_t shard, int32_t* halo_rows,
+                       int64_t halo_cap, int32_t* nbr_out, int32_t* extra_out, int64_t* h_n_halo,
+                       void* workspace, size_t ws_bytes, void* stream) {
+  return dist_halo_plan(nbr_loc, n_local, k, extra_ids, n_extra, N, row0, shard, halo_rows, halo_cap, nbr_out,
+                        extra_out, h_n_halo, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int osc_dist_halo_exchange(const osc_dist_t* dist, int32_t D, float* d_flag, void* stream) {
+  return dist_halo_exchange(dist, D, d_flag, static_cast<cudaStream_t>(stream));
+}
+int osc_dist_pcg_workspace(const osc_dist_t* dist, int64_t n_loc, int32_t D, size_t* h_bytes) {
+  return dist_pcg_workspace(dist, n_loc, D, h_bytes);
+}
+int osc_dist_pcg_solve(const osc_dist_t* dist, const osc_graph_t* g, const osc_chain_t* chain,
+                       const osc_params_t* prm, int32_t mode, float dt, int32_t warm_start, float inertia,
+                       int32_t jacobi, double tol, int32_t max_iters, const float* Y, const float* U,
+                       const float* psi, const float* gates, int32_t D, float* X, int32_t* h_iters,
+                       float* h_res, void* workspace, size_t ws_bytes, void* stream) {
+  return dist_pcg_solve(dist, g, chain, prm, mode, dt, warm_start, inertia, jacobi, tol, max_iters, Y, U, psi,
+                        gates, D, X, h_iters, h_res, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int osc_dist_delta_h(const osc_dist_t* dist, const osc_graph_t* g, const osc_chain_t* chain,
+                     const osc_params_t* prm, const float* U, const float* Ustar, const float* gates,
+                     int32_t D, double* h_deltaH, void* workspace, size_t ws_bytes, void* stream) {
+  return dist_delta_h(dist, g, chain, prm, U, Ustar, gates, D, h_deltaH, workspace, ws_bytes,
+                      static_cast<cudaStream_t>(stream));
 }
 
 int osc_batched_supported(int64_t N, int32_t D, int32_t k) { return batched_supported(N, D, k); }

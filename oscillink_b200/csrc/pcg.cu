@@ -12,7 +12,9 @@
 // block owns a contiguous row range, every thread keeps fp64 partial sums for its columns,
 // partials go to part[block][D] and a second tiny kernel reduces them in a fixed order
 // (run-to-run deterministic -- the stop test is a knife edge at large N).
-#include "common.cuh"
+#include <map>
+
+#include "pcg.cuh"
 
 namespace osc {
 
@@ -138,15 +140,7 @@ struct ChainView {
   const int32_t* slot;  // nullptr => no chain
 };
 
-// Where the gathered vector lives.  One GPU / all-gathered halo: `all` holds all N rows.  Row-sharded
-// P2P halo (osc_pcg_*_p2p): rank g's block of `shard` rows sits in peers[g], a buffer in GPU g's HBM
-// mapped into this process (CUDA IPC); remote rows are fetched by plain loads over NVLink inside the
-// SpMM, tile by tile, instead of an all-gather in front of it.
-struct VecView {
-  const float* all;           // [N][D] or nullptr
-  const float* const* peers;  // [world] device table of block base pointers, or nullptr
-  int64_t shard;
-};
+// VecView (pcg.cuh): where the gathered vector lives.
 __device__ __forceinline__ const float* row_ptr(const VecView& v, int64_t j, int D) {
   if (v.peers == nullptr) return v.all + j * D;
   const int64_t g = j / v.shard;
@@ -169,8 +163,9 @@ template <int VEC, bool RES0>
 __global__ void __launch_bounds__(256)
 pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
                 VecView vv, float* __restrict__ out, float* __restrict__ Pout,
-                double* __restrict__ part, int rch) {
+                double* __restrict__ part, int rch, const int* __restrict__ done) {
   extern __shared__ double sh[];
+  if (done != nullptr && *done != 0) return;  // the solve has stopped (pcg_decide): nothing to do
   const int CG = dm.D / VEC;
   const int nthr = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -194,7 +189,7 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
     __syncthreads();  // the previous chunk's readers are done
     for (int e = tid; e < rows * g.k; e += nthr) {
       const int32_t j = g.nbr[c0 * g.k + e];
-      s_nb[e] = j >= 0 ? row_ptr(vv, j, dm.D) : nullptr;
+      s_nb[e] = j >= 0 ? (vv.local_ids ? vv.all + (int64_t)j * dm.D : row_ptr(vv, j, dm.D)) : nullptr;
       s_w[e] = g.W[c0 * g.k + e];
     }
     for (int e = tid; e < rows; e += nthr) s_deg[e] = g.deg[c0 + e];
@@ -204,7 +199,7 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
       const int64_t i = c0 + lr;
       const int64_t gi = dm.row0 + i;
       float own[VEC], s[VEC];
-      ldv<VEC>(row_ptr(vv, gi, dm.D) + co, own);
+      ldv<VEC>((vv.local_ids ? vv.all + i * dm.D : row_ptr(vv, gi, dm.D)) + co, own);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s[v] = 0.f;
       const int n = s_deg[lr];
@@ -254,7 +249,8 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
           for (int v = 0; v < VEC; ++v) sp[v] = 0.f;
           for (int e = ch.rowptr[sl]; e < ch.rowptr[sl + 1]; ++e) {
             float x[VEC];
-            ldv<VEC>(row_ptr(vv, ch.col[e], dm.D) + co, x);
+            const int32_t cj = ch.col[e];
+            ldv<VEC>((vv.local_ids ? vv.all + (int64_t)cj * dm.D : row_ptr(vv, cj, dm.D)) + co, x);
             const float w = ch.Wp[e];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) sp[v] = fmaf(w, x[v], sp[v]);
@@ -291,8 +287,10 @@ __global__ void __launch_bounds__(256)
 pcg_update_kernel(Dims dm, Coef c, const float* __restrict__ gates, const float* __restrict__ rz,
                   const float* __restrict__ pap, const float* __restrict__ P,
                   const float* __restrict__ AP, float* __restrict__ X, float* __restrict__ R,
-                  double* __restrict__ part_rr, double* __restrict__ part_rz) {
+                  double* __restrict__ part_rr, double* __restrict__ part_rz,
+                  const int* __restrict__ done) {
   extern __shared__ double sh[];
+  if (done != nullptr && *done != 0) return;
   const int CG = dm.D / VEC;
   const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
   const int64_t r_beg = (int64_t)blockIdx.x * rpb;
@@ -336,7 +334,8 @@ template <int VEC>
 __global__ void pcg_pupdate_kernel(Dims dm, Coef c, const float* __restrict__ gates,
                                    const float* __restrict__ rz_new,
                                    const float* __restrict__ rz_old, const float* __restrict__ R,
-                                   float* __restrict__ P) {
+                                   float* __restrict__ P, const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
   const int CG = dm.D / VEC;
   const int64_t total = dm.n_local * CG;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -373,8 +372,9 @@ __global__ void diff_kernel(const float* __restrict__ a, const float* __restrict
 // on the bit pattern (values are >= 0; *d_max is zeroed by the host wrapper beforehand).
 __global__ void __launch_bounds__(1024)
 pcg_reduce_kernel(const double* __restrict__ part, int n_blocks, int D, float* __restrict__ out,
-                  float* __restrict__ d_max, double* __restrict__ out64) {
+                  float* __restrict__ d_max, double* __restrict__ out64, const int* __restrict__ done) {
   __shared__ double ssum[32][33];
+  if (done != nullptr && *done != 0) return;
   const int cx = threadIdx.x, ry = threadIdx.y;
   const int cidx = blockIdx.x * 32 + cx;
   double s = 0.0;
@@ -517,10 +517,9 @@ int pcg_max_ell_width(int D) {
   return (int)((kSpmmSmemMax - fixed) / 12);
 }
 
-static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
-                       const osc_chain_t* chain, const osc_params_t* prm, int mode, float dt,
-                       int jacobi, const float* gates, VecView vv, float* out, float* Pout,
-                       double* part, cudaStream_t st) {
+int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
+                const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates, VecView vv,
+                float* out, float* Pout, double* part, cudaStream_t st, const int* done) {
   if (d->n_local == 0) return OSC_OK;
   int vec;
   dim3 blk;
@@ -539,7 +538,7 @@ static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
       OSC_CUDA(cudaFuncSetAttribute((const void*)pcg_spmm_kernel<VEC, R0>,                                \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmmSmemMax));    \
     pcg_spmm_kernel<VEC, R0><<<grid, blk, smem, st>>>(to_dims(d), c, gview(g), cview(chain), gates, vv,  \
-                                                      out, Pout, part, rch);                              \
+                                                      out, Pout, part, rch, done);                        \
   })
   if (res0) {
     OSC_SPMM_LAUNCH(true)
@@ -554,7 +553,7 @@ static int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g,
 int pcg_residual0(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                   const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates,
                   const float* Xall, float* RBv, float* P, double* part_rz, cudaStream_t st) {
-  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, VecView{Xall, nullptr, 0}, RBv, P,
+  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, VecView{Xall, nullptr, 0, 0}, RBv, P,
                      part_rz, st);
 }
 
@@ -562,28 +561,28 @@ int pcg_residual0_p2p(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_c
                       const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates,
                       const float* const* peers, int64_t shard, float* RBv, float* P, double* part_rz,
                       cudaStream_t st) {
-  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, VecView{nullptr, peers, shard}, RBv, P,
+  return spmm_launch(true, d, g, chain, prm, mode, dt, jacobi, gates, VecView{nullptr, peers, shard, 0}, RBv, P,
                      part_rz, st);
 }
 
 int pcg_spmm_dot(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                  const osc_params_t* prm, int mode, float dt, const float* gates, const float* Pall,
-                 float* AP, double* part_pap, cudaStream_t st) {
-  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, VecView{Pall, nullptr, 0}, AP, nullptr,
-                     part_pap, st);
+                 float* AP, double* part_pap, cudaStream_t st, const int* done) {
+  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, VecView{Pall, nullptr, 0, 0}, AP, nullptr,
+                     part_pap, st, done);
 }
 
 int pcg_spmm_dot_p2p(const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                      const osc_params_t* prm, int mode, float dt, const float* gates,
                      const float* const* peers, int64_t shard, float* AP, double* part_pap, cudaStream_t st) {
-  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, VecView{nullptr, peers, shard}, AP, nullptr,
+  return spmm_launch(false, d, g, chain, prm, mode, dt, 1, gates, VecView{nullptr, peers, shard, 0}, AP, nullptr,
                      part_pap, st);
 }
 
 int pcg_reduce(const double* part, int n_blocks, int D, float* out, float* d_max, double* out64,
-               cudaStream_t st) {
+               cudaStream_t st, const int* done) {
   if (d_max != nullptr) OSC_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), st));
-  pcg_reduce_kernel<<<(D + 31) / 32, dim3(32, 32, 1), 0, st>>>(part, n_blocks, D, out, d_max, out64);
+  pcg_reduce_kernel<<<(D + 31) / 32, dim3(32, 32, 1), 0, st>>>(part, n_blocks, D, out, d_max, out64, done);
   OSC_LAUNCH_CHECK("pcg_reduce_kernel");
   return OSC_OK;
 }
@@ -591,7 +590,7 @@ int pcg_reduce(const double* part, int n_blocks, int D, float* out, float* d_max
 int pcg_update(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int jacobi,
                const float* gates, const float* rz, const float* pap, const float* P,
                const float* AP, float* X, float* R, double* part_rr, double* part_rz,
-               cudaStream_t st) {
+               cudaStream_t st, const int* done) {
   if (d->n_local == 0) return OSC_OK;
   int vec;
   dim3 blk;
@@ -600,14 +599,14 @@ int pcg_update(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float
   const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double);
   const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
   OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC><<<grid, blk, smem, st>>>(
-                            to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz);)
+                            to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz, done);)
   OSC_LAUNCH_CHECK("pcg_update_kernel");
   return OSC_OK;
 }
 
 int pcg_pupdate(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int jacobi,
                 const float* gates, const float* rz_new, const float* rz_old, const float* R,
-                float* P, cudaStream_t st) {
+                float* P, cudaStream_t st, const int* done) {
   if (d->n_local == 0) return OSC_OK;
   int vec;
   dim3 blk;
@@ -615,13 +614,92 @@ int pcg_pupdate(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, floa
   Coef c = make_coef(prm, mode, dt, jacobi);
   const int64_t total = d->n_local * (d->D / vec);
   OSC_VEC_DISPATCH(vec, pcg_pupdate_kernel<VEC><<<ew_grid(total), 256, 0, st>>>(
-                            to_dims(d), c, gates, rz_new, rz_old, R, P);)
+                            to_dims(d), c, gates, rz_new, rz_old, R, P, done);)
   OSC_LAUNCH_CHECK("pcg_pupdate_kernel");
   return OSC_OK;
 }
 
+// ---------------------------------------------------------------- stop test on the device
+__global__ void __launch_bounds__(256) pcg_decide_kernel(PcgCtl* ctl, const float* __restrict__ rr,
+                                                         const float* __restrict__ d_res, int D, double tol,
+                                                         int it, int max_iters) {
+  if (ctl->done != 0) return;
+  __shared__ float smax[256];
+  float mx = 0.f;
+  if (rr != nullptr) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) mx = fmaxf(mx, __fsqrt_rn(fmaxf(rr[c], 0.f)));
+  } else if (threadIdx.x == 0) {
+    mx = *d_res;
+  }
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float res = smax[0];
+    ctl->res = res;
+    ctl->iters = it;
+    if ((double)res <= tol || it >= max_iters) ctl->done = 1;  // solver.py:29-31
+  }
+}
+
+int pcg_decide(PcgCtl* ctl, const float* rr, const float* d_res, int D, double tol, int it, int max_iters,
+               cudaStream_t st) {
+  pcg_decide_kernel<<<1, 256, 0, st>>>(ctl, rr, d_res, D, tol, it, max_iters);
+  OSC_LAUNCH_CHECK("pcg_decide_kernel");
+  return OSC_OK;
+}
+
+int launch_diff(const float* a, const float* b, float* out, int64_t n, cudaStream_t st) {
+  if (n == 0) return OSC_OK;
+  diff_kernel<<<ew_grid(n), 256, 0, st>>>(a, b, out, n);
+  OSC_LAUNCH_CHECK("diff_kernel");
+  return OSC_OK;
+}
+
+int launch_sum_doubles(const double* v, int D, double* total, cudaStream_t st) {
+  sum_doubles_kernel<<<1, 1024, 0, st>>>(v, D, total);
+  OSC_LAUNCH_CHECK("sum_doubles_kernel");
+  return OSC_OK;
+}
+
+// ---------------------------------------------------------------- lagged host poll of the control block
+int CtlPoll::init() {
+  if (h != nullptr) return OSC_OK;
+  OSC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h), 2 * sizeof(PcgCtl), cudaHostAllocDefault));
+  for (int i = 0; i < 2; ++i) OSC_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  return OSC_OK;
+}
+int CtlPoll::record(int it, const PcgCtl* d_ctl, cudaStream_t st) {
+  OSC_CUDA(cudaMemcpyAsync(&h[it & 1], d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, st));
+  OSC_CUDA(cudaEventRecord(ev[it & 1], st));
+  return OSC_OK;
+}
+int CtlPoll::wait(int it, PcgCtl* out) {
+  OSC_CUDA(cudaEventSynchronize(ev[it & 1]));
+  *out = h[it & 1];
+  return OSC_OK;
+}
+CtlPoll* ctl_poll() {
+  // one set of pinned slots + events per host thread and device; never freed (a few bytes per thread)
+  static thread_local std::map<int, CtlPoll> polls;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  CtlPoll& p = polls[dev];
+  if (p.init() != OSC_OK) return nullptr;
+  return &p;
+}
+
 // The recurrences of solver.py:19-37 from a caller-supplied start: on entry X = x0 and R = right-hand
 // side; on exit X = last iterate, R = recurrence residual.  Workspace: P, AP, partials, column sums.
+// The stop test runs on the device (pcg_decide) and the host enqueues ONE iteration ahead of it: the
+// kernels of an iteration that follows the stop return at once, so the result is the reference's and
+// the stream never drains between iterations.
 static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_chain_t* chain,
                     const osc_params_t* prm, int mode, float dt, int jacobi, double tol, int max_iters,
                     const float* gates, float* X, float* R, Arena& ar, int* h_iters, float* h_res,
@@ -636,31 +714,41 @@ static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_cha
   float* rz_new = ar.take<float>(D);
   float* pap = ar.take<float>(D);
   float* rr = ar.take<float>(D);
-  float* d_res = ar.take<float>(64);
+  float* d_res = ar.take<float>(32);
+  PcgCtl* ctl = ar.take<PcgCtl>(1);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "pcg: workspace too small");
-  int rc, it = 0;
-  float res = __builtin_nanf("");
+  CtlPoll* poll = ctl_poll();
+  if (poll == nullptr) return OSC_ERR_CUDA;
+  const int* done = &ctl->done;
+  int rc;
+  OSC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PcgCtl), st));
   if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) return rc;
   if ((rc = pcg_reduce(part_a, d.n_blocks, D, rz, nullptr, nullptr, st))) return rc;
+  PcgCtl h{0, 0, __builtin_nanf(""), 0};
+  int it = 0;
   for (it = 1; it <= max_iters; ++it) {
-    if ((rc = pcg_spmm_dot(&d, g, chain, prm, mode, dt, gates, P, AP, part_a, st))) return rc;
-    if ((rc = pcg_reduce(part_a, d.n_blocks, D, pap, nullptr, nullptr, st))) return rc;
-    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, X, R, part_a, part_b, st)))
+    if ((rc = pcg_spmm_dot(&d, g, chain, prm, mode, dt, gates, P, AP, part_a, st, done))) return rc;
+    if ((rc = pcg_reduce(part_a, d.n_blocks, D, pap, nullptr, nullptr, st, done))) return rc;
+    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, X, R, part_a, part_b, st, done)))
       return rc;
-    if ((rc = pcg_reduce(part_a, d.n_blocks, D, rr, d_res, nullptr, st))) return rc;
-    if ((rc = pcg_reduce(part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st))) return rc;
-    OSC_CUDA(cudaMemcpyAsync(&res, d_res, sizeof(float), cudaMemcpyDeviceToHost, st));
-    OSC_CUDA(cudaStreamSynchronize(st));
-    if ((double)res <= tol) break;  // solver.py:29-31
+    if ((rc = pcg_reduce(part_a, d.n_blocks, D, rr, d_res, nullptr, st, done))) return rc;
+    if ((rc = pcg_reduce(part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st, done))) return rc;
+    if ((rc = pcg_decide(ctl, nullptr, d_res, D, tol, it, max_iters, st))) return rc;
+    if ((rc = poll->record(it, ctl, st))) return rc;
+    if (it > 1) {  // the previous iteration's verdict has landed (or lands while this one runs)
+      if ((rc = poll->wait(it - 1, &h))) return rc;
+      if (h.done) break;
+    }
     if (it == max_iters) break;
-    if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st))) return rc;
+    if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st, done))) return rc;
     float* t = rz;
     rz = rz_new;
     rz_new = t;
   }
   if (it > max_iters) it = max_iters;
-  if (h_iters) *h_iters = it;
-  if (h_res) *h_res = res;
+  if (!h.done && (rc = poll->wait(it, &h))) return rc;  // the last enqueued iteration decides
+  if (h_iters) *h_iters = h.iters;
+  if (h_res) *h_res = h.res;
   return OSC_OK;
 }
 

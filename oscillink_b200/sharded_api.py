@@ -26,7 +26,12 @@ Solve (solver.py:15-37), two exact partitions of the same recurrences:
                  (osc_pcg_spmm_dot_p2p), so there is no all-gather and no N x D staging buffer --
                  only a stream-ordered barrier between "p written" and "p read by peers".
 
-The per-iteration kernels are the exported phase entry points of the C ABI (osc_pcg_*).
+Under NCCL the whole solve is ONE call into the C ABI (osc_dist_pcg_solve, csrc/dist.cu): NCCL is called
+from C on the current stream and the stop test runs on the device.  halo="pull" (rows partition): every
+rank pulls the unique remote rows its graph references from the peers' blocks over NVLink (CUDA IPC
+mappings) -- one fetch per ROW, ascending, instead of the all-gather's every row or the fused kernel's
+one fetch per REFERENCE.  Without NCCL (gloo: the CPU / single-device test rigs) the same recurrences are
+driven from Python through the exported phase entry points (osc_pcg_*), `pcg_schedule` below.
 """
 from __future__ import annotations
 
@@ -319,6 +324,85 @@ class _PeerBuffers:
         self._own, self._opened = [], []
 
 
+class _PullHalo:
+    """State of the OSC_HALO_PULL strategy for one rank: the halo plan (osc_dist_halo_plan) and the
+    peer-mapped block [shard own rows | n_halo pulled rows][D] whose first `shard` rows every peer maps with
+    CUDA IPC (osc_peer_alloc / osc_peer_open).  Collective: every rank builds it at the same point."""
+
+    def __init__(self, lat: "ShardedLattice"):
+        import torch
+        import torch.distributed as dist
+
+        cabi, lib, dev = _cabi_mod(), lat._lib, lat._dev
+        self._lib, self._cabi, self.group, self.world = lib, cabi, lat.group, lat.world
+        st = torch.cuda.current_stream().cuda_stream
+        r0, nl, k = lat.row0, lat.n_local, lat.k
+        nbr_loc = lat._nbr[r0:r0 + nl].contiguous()
+        extra = lat._chain["col"] if lat._chain is not None else None
+        n_extra = int(extra.numel()) if extra is not None else 0
+        need = C.c_size_t(0)
+        cabi.check(lib.osc_dist_halo_plan_workspace(lat.N, C.byref(need)))
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+        n_halo = C.c_int64(0)
+        args = (nbr_loc.data_ptr() if nl else None, nl, k, extra.data_ptr() if n_extra else None, n_extra,
+                lat.N, r0, lat.shard)
+        cabi.check(lib.osc_dist_halo_plan(*args, None, 0, None, None, C.byref(n_halo), ws.data_ptr(),
+                                          ws.numel(), st), "osc_dist_halo_plan")
+        self.n_halo = int(n_halo.value)
+        self.halo_rows = torch.empty(max(self.n_halo, 1), dtype=torch.int32, device=dev)
+        self.nbr_local = torch.full((max(nl, 1), k), -1, dtype=torch.int32, device=dev)
+        self.chain_col = torch.empty(max(n_extra, 1), dtype=torch.int32, device=dev)
+        cabi.check(lib.osc_dist_halo_plan(*args, self.halo_rows.data_ptr(), self.n_halo,
+                                          self.nbr_local.data_ptr(), self.chain_col.data_ptr() if n_extra else None,
+                                          C.byref(n_halo), ws.data_ptr(), ws.numel(), st), "osc_dist_halo_plan")
+        del ws
+        rows = max(lat.shard + self.n_halo, 1)
+        ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+        cabi.check(lib.osc_peer_alloc(rows * lat.D * 4, C.byref(ptr), h), "osc_peer_alloc")
+        self.block_ptr, self._opened = ptr.value, []
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (lat.rank, dev.index, bytes(h)), group=self.group)
+        tab = [0] * self.world
+        for rank, dev_index, hb in everyone:
+            if rank == lat.rank:
+                tab[rank] = self.block_ptr
+                continue
+            if dev_index != dev.index:
+                cabi.check(lib.osc_enable_peer_access(dev_index), "osc_enable_peer_access")
+            p = C.c_void_p()
+            cabi.check(lib.osc_peer_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)), "osc_peer_open")
+            self._opened.append(p.value)
+            tab[rank] = p.value
+        self.tab = torch.tensor(tab, dtype=torch.int64, device=dev)
+        self.halo_fraction = self.n_halo / max(lat.N - nl, 1)  # share of the remote rows that is needed
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def chain_struct(self, chain):
+        c = self._cabi.Chain
+        return c(chain["n_rows"], chain["nnz"], chain["rows"].data_ptr(), chain["rowptr"].data_ptr(),
+                 self.chain_col.data_ptr(), chain["Wp"].data_ptr(), chain["Ap"].data_ptr(),
+                 chain["slot"].data_ptr())
+
+    def close(self) -> None:
+        """Unmap the peers' blocks and free this rank's (collective)."""
+        import torch
+        import torch.distributed as dist
+
+        if self.block_ptr is None:
+            return
+        torch.cuda.synchronize()
+        try:
+            dist.barrier(group=self.group)  # nobody is still reading a block that is about to be freed
+        except Exception:
+            pass
+        for p in self._opened:
+            self._lib.osc_peer_close(C.c_void_p(p))
+        self._lib.osc_peer_free(C.c_void_p(self.block_ptr))
+        self.block_ptr, self._opened = None, []
+
+
+
 def _cabi_mod():
     from . import _cabi
 
@@ -331,7 +415,7 @@ class ShardedLattice:
 
     def __init__(self, Y_local, N: int, kneighbors: int = 6, row_cap_val: float = 1.0, lamG: float = 1.0,
                  lamC: float = 0.5, lamQ: float = 4.0, *, mode: str = "rows", group=None,
-                 knn_engine: int = 0, p2p: bool | None = None):
+                 knn_engine: int = 0, p2p: bool | None = None, halo: str | None = None):
         import torch
         import torch.distributed as dist
 
@@ -371,9 +455,17 @@ class ShardedLattice:
         self._chain = None
         self._chain_nodes = None
         self._engine = knn_engine
-        self._p2p_arg = p2p  # resolved after the build (needs nnz), see _resolve_halo
+        if halo not in (None, "allgather", "pull", "fused"):
+            raise ValueError("halo must be None, 'allgather', 'pull' or 'fused'")
+        if halo is None and p2p is not None:  # legacy switch: p2p=True is the fused kernel
+            halo = "fused" if p2p else "allgather"
+        self._halo_arg = halo  # resolved after the build, see _resolve_halo
+        self.halo = "allgather"
         self._want_p2p = False
         self._peers = None
+        self._pull = None
+        self._comm = None      # ncclComm_t of the C-ABI solve (None: not tried yet, 0: unavailable)
+        self._comm_owned = False
         self.last: dict[str, Any] = {"iters": 0, "res": None, "t_ms": None}
         self.timings: dict[str, float] = {}
         self._build(Y_local)
@@ -456,25 +548,32 @@ class ShardedLattice:
         self.timings["graph_build_ms"] = 1000.0 * (time.time() - t0)
 
     def _resolve_halo(self) -> None:
-        """Halo strategy of the rows partition.  p2p=True / False force the fused P2P halo / the NCCL
-        all-gather.  Auto (None): the fused kernel fetches a remote row once per REFERENCE
-        (nnz/N * (G-1)/G rows per local row over NVLink), the all-gather once per ROW ((G-1) rows per
-        local row), so fusing moves fewer bytes only when nnz/N < G; kNN graphs of random anchors
-        have no locality, hence no better bound (measured: N=1M k=16 on 2 GPUs, 21.0 ms fused vs
-        3.3 + 4.4 ms all-gather + SpMM)."""
+        """Halo strategy of the rows partition: "allgather" (NCCL all-gather of p in front of every SpMM),
+        "pull" (unique remote rows fetched over NVLink peer memory into a local halo block, C path only) or
+        "fused" (remote rows read inside the SpMM, once per reference: measured 7x slower than the
+        all-gather on kNN graphs of random anchors, kept for graphs with locality).  Auto: "pull" under NCCL,
+        "allgather" otherwise."""
         import torch.distributed as dist
 
+        nccl = self.world > 1 and dist.is_initialized() and dist.get_backend(self.group) == "nccl"
         if self.world <= 1:
-            self._want_p2p = False
-        elif self._p2p_arg is None:
-            nccl = dist.is_initialized() and dist.get_backend(self.group) == "nccl"
-            self._want_p2p = bool(nccl and float(self.nnz.item()) / max(self.N, 1) < self.world)
+            self.halo = "allgather"
+        elif self._halo_arg is None:
+            self.halo = "pull" if nccl else "allgather"
         else:
-            self._want_p2p = bool(self._p2p_arg)
+            self.halo = self._halo_arg
+        if self.halo == "pull" and not nccl:
+            self.halo = "allgather"  # the pull halo lives in the C path, which needs NCCL
+        self._want_p2p = self.halo == "fused"
 
-    def set_halo(self, p2p: bool | None) -> None:
-        """Switch the rows-partition halo strategy on a built lattice (collective)."""
-        self._p2p_arg = p2p
+    def set_halo(self, halo) -> None:
+        """Switch the rows-partition halo strategy on a built lattice (collective).  Accepts the strategy
+        name or the legacy bool (True = fused P2P, False = all-gather)."""
+        if isinstance(halo, bool):
+            halo = "fused" if halo else "allgather"
+        if halo not in (None, "allgather", "pull", "fused"):
+            raise ValueError("halo must be None, 'allgather', 'pull' or 'fused'")
+        self._halo_arg = halo
         self._resolve_halo()
 
     def close(self) -> None:
@@ -482,6 +581,15 @@ class ShardedLattice:
         if self._peers is not None:
             self._peers.close()
             self._peers = None
+        if self._pull is not None:
+            self._pull.close()
+            self._pull = None
+        if self._comm and self._comm_owned:
+            import torch
+
+            torch.cuda.synchronize()
+            self._lib.osc_dist_comm_destroy(C.c_void_p(self._comm))
+        self._comm, self._comm_owned = None, False
 
     def repartition(self, mode: str) -> None:
         """Switch between the row-block and the column-slab partition WITHOUT rebuilding the graph
@@ -593,9 +701,91 @@ class ShardedLattice:
         self.lamP = float(lamP)
         self._chain_nodes = list(map(int, chain))
         self._Ustar = None
+        if self._pull is not None:  # the chain's columns join the halo plan
+            self._pull.close()
+            self._pull = None
 
     def _psi_view(self):
         return self._dpsi if self.mode == "rows" else self._dpsi[self.c0:self.c0 + self.Dl].contiguous()
+
+    # ---- NCCL communicator of the C-ABI solve
+    def _nccl_comm(self):
+        """ncclComm_t for osc_dist_* (0 if the C path cannot be used: no NCCL backend / binding failed).
+        The library creates its own communicator (ncclGetUniqueId on rank 0, the 128-byte id broadcast
+        through torch.distributed, ncclCommInitRank on every rank); if that fails, torch's own communicator
+        of this group is borrowed (same NCCL library instance)."""
+        import torch
+        import torch.distributed as dist
+
+        if self._comm is not None:
+            return self._comm
+        self._comm = 0
+        if self.world <= 1 or not dist.is_initialized() or dist.get_backend(self.group) != "nccl":
+            return self._comm
+        lib = self._lib
+        ok = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        try:
+            box = [None]
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                box[0] = bytes(buf) if lib.osc_dist_unique_id(buf) == 0 else None
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=self.group)
+            if box[0] is not None:
+                comm = C.c_void_p()
+                idb = (C.c_ubyte * 128).from_buffer_copy(box[0])
+                if lib.osc_dist_comm_init(idb, self.world, self.rank, C.byref(comm)) == 0 and comm.value:
+                    self._comm, self._comm_owned = comm.value, True
+                    ok += 1
+        except Exception:
+            pass
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all ranks or none
+        if int(ok.item()) == 0:
+            if self._comm and self._comm_owned:
+                lib.osc_dist_comm_destroy(C.c_void_p(self._comm))
+            self._comm, self._comm_owned = 0, False
+            try:  # borrow torch's communicator
+                pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+                self._comm = int(pg._get_backend(self._dev)._comm_ptr())
+            except Exception:
+                self._comm = 0
+        return self._comm
+
+    def _dist_struct(self):
+        cabi = self._cabi
+        rows = self.mode == "rows"
+        pull = rows and self.world > 1 and self.halo == "pull"
+        if pull and self._pull is None:
+            self._pull = _PullHalo(self)
+        ds = cabi.Dist(self._nccl_comm() or None, self.world, self.rank,
+                       cabi.PART_ROWS if rows else cabi.PART_COLUMNS,
+                       cabi.HALO_PULL if pull else cabi.HALO_ALLGATHER, self.N, self.shard,
+                       None, None, None, None, 0)
+        if pull:
+            pl = self._pull
+            ds.d_peer_P, ds.P_block = pl.tab.data_ptr(), pl.block_ptr
+            ds.halo_rows = pl.halo_rows.data_ptr() if pl.n_halo else None
+            ds.halo_nbr, ds.n_halo = pl.nbr_local.data_ptr(), pl.n_halo
+        return ds
+
+    def _use_c_path(self) -> bool:
+        """The C-ABI solve: always on one GPU, and under NCCL unless the fused-P2P halo was asked for."""
+        if self.world == 1:
+            return True
+        if self.mode == "rows" and self.halo == "fused":
+            return False
+        return bool(self._nccl_comm())
+
+    def _c_args(self):
+        rows = self.mode == "rows"
+        g = self._graph_struct(local=rows)
+        ch = self._chain_struct()
+        if ch is not None and rows and self.world > 1 and self.halo == "pull":
+            ch = self._pull.chain_struct(self._chain)  # column ids as rows of the block
+        gates = self._dB_loc if rows else self._dB_all
+        Dl = self.D if rows else self.Dl
+        n_loc = self.n_local if rows else self.N
+        return g, ch, gates, Dl, n_loc
 
     def _solve(self, mode_id: int, dt: float, tol: float, max_iters: int, jacobi: bool = True,
                warm_start: bool = True, inertia: float = 0.0):
@@ -603,11 +793,30 @@ class ShardedLattice:
 
         cabi, lib = self._cabi, self._lib
         rows = self.mode == "rows"
+        if self._use_c_path():
+            ds = self._dist_struct()  # (collective on first use: communicator, halo plan)
+            g, ch, gates, Dl, n_loc = self._c_args()
+            prm = self._params_struct()
+            psi = self._psi_view()
+            X = torch.empty_like(self._Y)
+            need = C.c_size_t(0)
+            cabi.check(lib.osc_dist_pcg_workspace(C.byref(ds), n_loc, Dl, C.byref(need)), "osc_dist_pcg_workspace")
+            ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self._dev)
+            it, res = C.c_int32(0), C.c_float(0.0)
+            cabi.check(lib.osc_dist_pcg_solve(
+                C.byref(ds), C.byref(g), C.byref(ch) if ch is not None else None, C.byref(prm), mode_id,
+                float(dt), 1 if warm_start else 0, float(inertia), 1 if jacobi else 0, float(tol),
+                int(max_iters), self._Y.data_ptr(), self._U.data_ptr(), psi.data_ptr(), gates.data_ptr(), Dl,
+                X.data_ptr(), C.byref(it), C.byref(res), ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream().cuda_stream), "osc_dist_pcg_solve")
+            return X, int(it.value), float(res.value)
+        # ---- no NCCL (gloo test rigs) or the fused-P2P halo: the phase entry points driven from Python
         use_p2p = rows and self._want_p2p
         if use_p2p and self._peers is None:
             self._peers = _PeerBuffers(self)
         if not use_p2p and self._peers is not None and rows:
-            self.close()  # halo strategy switched back to the all-gather
+            self._peers.close()  # halo strategy switched back to the all-gather
+            self._peers = None
         X = self._peers.X[: self.n_local] if use_p2p else torch.empty_like(self._Y)
         Bv = torch.empty_like(self._Y)
         Dl = self.D if rows else self.Dl
@@ -653,6 +862,20 @@ class ShardedLattice:
         import torch.distributed as dist
 
         Us = self.solve_Ustar()
+        if self._use_c_path():
+            cabi, lib = self._cabi, self._lib
+            ds = self._dist_struct()
+            g, ch, gates, Dl, n_loc = self._c_args()
+            prm = self._params_struct()
+            need = C.c_size_t(0)
+            cabi.check(lib.osc_dist_pcg_workspace(C.byref(ds), n_loc, Dl, C.byref(need)), "osc_dist_pcg_workspace")
+            ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self._dev)
+            out = C.c_double(0.0)
+            cabi.check(lib.osc_dist_delta_h(
+                C.byref(ds), C.byref(g), C.byref(ch) if ch is not None else None, C.byref(prm),
+                self._U.data_ptr(), Us.data_ptr(), gates.data_ptr(), Dl, C.byref(out), ws.data_ptr(),
+                ws.numel(), torch.cuda.current_stream().cuda_stream), "osc_dist_delta_h")
+            return float(np.float32(out.value))
         diff = self._U - Us
         if self.mode == "rows" and self._peers is not None and self._want_p2p:
             # fused halo: U - U* goes into the peer-mapped P block and the SpMM reads the peers' blocks
@@ -682,6 +905,29 @@ class ShardedLattice:
                      "avg_degree": float(int((self._A > 0).sum().item()) / max(self.N, 1)),
                      "world_size": self.world, "partition": self.mode},
         }
+
+    def rows_of(self, t, ids):
+        """Full-width rows `ids` (global row ids, 1-D int64 tensor, same on every rank) of a state tensor
+        held in this lattice's partition (Y / U / U*), on every rank: [len(ids), D] fp32."""
+        import torch
+        import torch.distributed as dist
+
+        ids = ids.to(self._dev).long()
+        if self.world == 1:
+            return t[ids]
+        if self.mode == "rows":
+            out = torch.zeros((ids.numel(), self.D), dtype=t.dtype, device=self._dev)
+            mine = (ids >= self.row0) & (ids < self.row0 + self.n_local)
+            if bool(mine.any()):
+                out[mine] = t[ids[mine] - self.row0]
+            dist.all_reduce(out, group=self.group)  # the other ranks add exact zeros
+            return out
+        part = t[ids].contiguous()  # [R, Dl]
+        if dist.get_backend(self.group) == "gloo":
+            part = part.cpu()
+        parts = [torch.empty_like(part) for _ in range(self.world)]
+        dist.all_gather(parts, part, group=self.group)
+        return torch.cat(parts, dim=1).to(self._dev)
 
     # ---- host views for tests / callers
     def U_full(self) -> np.ndarray:
