@@ -156,6 +156,20 @@ int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batc
                             float* top_sim, float* gap, int32_t* d_n_flagged, void* workspace,
                             size_t ws_bytes, void* stream);
 
+/* As osc_knn_rescore_checked with a bound on the exhaustive path: if MORE than exhaustive_limit rows are
+ * flagged (exhaustive_limit < 0: no bound) the exhaustive scans are skipped, the flagged rows keep the
+ * result of their (possibly incomplete) candidate list, and the caller -- who reads *d_n_flagged -- re-runs
+ * the candidate pass with a tighter engine (OSC_KNN_TC, eps = OSC_KNN_EPS).  This is what keeps the
+ * single-product engines safe on clustered / near-duplicate anchors, where many rows have neighbours
+ * closer than their error bound.  osc_knn_exhaustive_limit(rows) = max(64, rows / 100) is the bound the
+ * library's own build flows use. */
+int osc_knn_rescore_guarded(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
+                            int64_t row0, int64_t N, int32_t D, const int32_t* cand_idx,
+                            const float* cand_sim, int32_t kc, int32_t k, float eps, int64_t exhaustive_limit,
+                            int32_t* top_idx, float* top_sim, float* gap, int32_t* d_n_flagged,
+                            void* workspace, size_t ws_bytes, void* stream);
+int64_t osc_knn_exhaustive_limit(int64_t rows);
+
 /* K1b -- graph.py:50-52 (S>0 filter), :64-65 (mutual), :77-83 (row cap), :87-92 (degree,
  * normalised weights).  top_idx/top_sim are the directed lists of ALL N rows of each lattice.
  * scratch: N*batch floats.  nnz: [batch] int64 (device). */

@@ -84,6 +84,10 @@ PROTOTYPES = {
     "osc_knn_rescore_checked": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i32, c_void_p,
                                           c_void_p, c_i32, c_i32, c_f32, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "osc_knn_rescore_guarded": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i32, c_void_p,
+                                          c_void_p, c_i32, c_i32, c_f32, c_i64, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "osc_knn_exhaustive_limit": (c_i64, [c_i64]),
     "osc_graph_assemble": (C.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_f32, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osc_knn_build_workspace": (C.c_int, [c_i64, c_i64, c_i32, c_i32, c_i32, P(c_size_t)]),

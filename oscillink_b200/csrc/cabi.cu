@@ -49,7 +49,8 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
                   int64_t batch, int64_t n_rows, int64_t row0, int64_t N, int D, int kc,
                   int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st, bool f16 = false);
 int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, const int32_t*,
-                   const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t);
+                   const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t,
+                   int64_t exhaustive_limit = -1);
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
                     int32_t*, float*, int64_t*, float*, cudaStream_t);
 int launch_receipt_full(const osc_graph_t*, const osc_params_t*, const float*, const float*,
@@ -243,11 +244,11 @@ int osc_knn_rescore_workspace(int64_t batch, int64_t n_rows, size_t* h_bytes) {
   return OSC_OK;
 }
 
-int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
+int osc_knn_rescore_guarded(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
                             int64_t row0, int64_t N, int32_t D, const int32_t* cand_idx,
-                            const float* cand_sim, int32_t kc, int32_t k, float eps, int32_t* top_idx,
-                            float* top_sim, float* gap, int32_t* d_n_flagged, void* workspace,
-                            size_t ws_bytes, void* stream) {
+                            const float* cand_sim, int32_t kc, int32_t k, float eps, int64_t exhaustive_limit,
+                            int32_t* top_idx, float* top_sim, float* gap, int32_t* d_n_flagged,
+                            void* workspace, size_t ws_bytes, void* stream) {
   OSC_REQUIRE(Yn_q && Yn_all && cand_idx && cand_sim && top_idx && top_sim && d_n_flagged,
               "knn_rescore_checked: NULL argument");
   OSC_REQUIRE(k >= 1 && kc >= k && batch <= 65535 && eps >= 0.f, "knn_rescore_checked: need 1 <= k <= kc");
@@ -259,7 +260,21 @@ int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batc
   OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * batch * n_rows * k, st));
   OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * batch * n_rows * k, st));
   return launch_rescore(Yn_q, Yn_all, batch, n_rows, row0, N, D, cand_idx, cand_sim, kc, k, eps, top_idx,
-                        top_sim, gap, static_cast<int64_t*>(workspace), d_n_flagged, st);
+                        top_sim, gap, static_cast<int64_t*>(workspace), d_n_flagged, st, exhaustive_limit);
+}
+
+int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
+                            int64_t row0, int64_t N, int32_t D, const int32_t* cand_idx,
+                            const float* cand_sim, int32_t kc, int32_t k, float eps, int32_t* top_idx,
+                            float* top_sim, float* gap, int32_t* d_n_flagged, void* workspace,
+                            size_t ws_bytes, void* stream) {
+  return osc_knn_rescore_guarded(Yn_q, Yn_all, batch, n_rows, row0, N, D, cand_idx, cand_sim, kc, k, eps, -1,
+                                 top_idx, top_sim, gap, d_n_flagged, workspace, ws_bytes, stream);
+}
+
+int64_t osc_knn_exhaustive_limit(int64_t rows) {
+  const int64_t one_percent = rows / 100;
+  return one_percent > 64 ? one_percent : 64;
 }
 
 int osc_graph_assemble(const int32_t* top_idx, const float* top_sim, int64_t batch, int64_t N, int32_t k,
@@ -361,17 +376,26 @@ int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int3
   }
   int eng = pick_engine(flags, N, N, D, k);
   if (eng < 0) eng = OSC_KNN_TC;  // osc_knn_build reports the error; size for the larger layout
-  const int kc = candidate_width(N, k, eng);
   const size_t rows = (size_t)batch * N;
-  size_t b = align_up(rows * D * sizeof(float));                       // Yn
-  if (eng == OSC_KNN_TC) b += 2 * align_up(rows * D * sizeof(float));  // hi, lo
-  if (eng == OSC_KNN_TC1) b += align_up(rows * D * sizeof(float));     // hi
-  if (eng == OSC_KNN_TCH) b += align_up(rows * D * 2);                 // fp16 rows
-  b += align_up(rows * kc * sizeof(int32_t)) + align_up(rows * kc * sizeof(float));  // candidates
-  b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
-  b += align_up(rows * sizeof(float));                                               // cap scale
-  b += align_up(rows * sizeof(int64_t)) + 512;                                       // flagged rows + counter
-  *h_bytes = b + 1024;
+  auto layout = [&](int e) {
+    const int kc = candidate_width(N, k, e);
+    size_t b = align_up(rows * D * sizeof(float));                     // Yn
+    if (e == OSC_KNN_TC) b += 2 * align_up(rows * D * sizeof(float));  // hi, lo
+    if (e == OSC_KNN_TC1) b += align_up(rows * D * sizeof(float));     // hi
+    if (e == OSC_KNN_TCH) b += align_up(rows * D * 2);                 // fp16 rows
+    b += align_up(rows * kc * sizeof(int32_t)) + align_up(rows * kc * sizeof(float));  // candidates
+    b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
+    b += align_up(rows * sizeof(float));                                               // cap scale
+    b += align_up(rows * sizeof(int64_t)) + 512;                                       // flagged rows + counter
+    return b + 1024;
+  };
+  size_t b = layout(eng);
+  // a single-product engine may hand the build over to the 3xTF32 engine (see osc_knn_build)
+  if ((eng == OSC_KNN_TC1 || eng == OSC_KNN_TCH) && knn_tc_supported(N, D, candidate_width(N, k, OSC_KNN_TC))) {
+    const size_t b3 = layout(OSC_KNN_TC);
+    if (b3 > b) b = b3;
+  }
+  *h_bytes = b;
   return OSC_OK;
 }
 
@@ -402,8 +426,16 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   int rc = osc_knn_build_workspace(batch, N, D, k, flags, &need);
   if (rc) return rc;
   if (ws_bytes < need) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
-  const int eng = pick_engine(flags, N, N, D, k);
+  int eng = pick_engine(flags, N, N, D, k);
   if (eng < 0) return fail(OSC_ERR_UNSUPPORTED, "knn_build: tensor-core engine does not cover this shape");
+  // Engine robustness: the single-product engines prove a row's candidate list complete only if the k-th
+  // exact score clears the list's tail by eps = 1.25e-3; on clustered / near-duplicate anchors many rows
+  // fail that test and would each cost an exhaustive N*D fp64 scan.  When more than max(64, 1 %) of the
+  // rows are flagged, the exhaustive pass is skipped and the candidate pass is re-run ONCE with the 3xTF32
+  // engine (eps = 1e-5), whose flagged rows (true near-ties only) then do take the exhaustive path.
+  const bool may_fall_back = (eng == OSC_KNN_TC1 || eng == OSC_KNN_TCH) &&
+                             knn_tc_supported(N, D, candidate_width(N, k, OSC_KNN_TC));
+  for (int attempt = 0; attempt < 2; ++attempt) {
   const int kc = candidate_width(N, k, eng);
   Arena ar(workspace, ws_bytes);
   float* Yn = ar.take<float>(rows * D);
@@ -429,10 +461,23 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
     return rc;
   OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * rows * k, st));
   OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * rows * k, st));
+  const bool guarded = may_fall_back && attempt == 0;
+  const int64_t limit = guarded ? osc_knn_exhaustive_limit((int64_t)rows) : -1;
   if ((rc = launch_rescore(Yn, Yn, batch, N, 0, N, D, cand_idx, cand_sim, kc, k, engine_eps(eng), top_idx,
-                           top_sim, gap, flagged, n_flagged, st)))
+                           top_sim, gap, flagged, n_flagged, st, limit)))
     return rc;
+  if (guarded) {
+    int h_flagged = 0;
+    OSC_CUDA(cudaMemcpyAsync(&h_flagged, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OSC_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)h_flagged > limit) {
+      eng = OSC_KNN_TC;
+      continue;
+    }
+  }
   return launch_assemble(top_idx, top_sim, batch, N, k, row_cap, nbr, A, W, deg, sqrt_deg, nnz, cscale, st);
+  }
+  return fail(OSC_ERR_CUDA, "knn_build: unreachable");
 }
 
 // ------------------------------------------------------------------ PCG

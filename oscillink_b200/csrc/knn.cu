@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256)
 knn_exact_rows_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall, int64_t n_rows,
                       int64_t row0, int64_t N, int D, int k, const int64_t* __restrict__ flagged,
                       const int* __restrict__ n_flagged, int32_t* __restrict__ top_idx,
-                      float* __restrict__ top_sim, float* __restrict__ gap) {
+                      float* __restrict__ top_sim, float* __restrict__ gap, int64_t limit) {
   extern __shared__ float smem[];
   const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = k + 1;
@@ -362,6 +362,9 @@ knn_exact_rows_kernel(const float* __restrict__ Yq, const float* __restrict__ Ya
   int* li = reinterpret_cast<int*>(smem + (size_t)warps * L) + (size_t)w * L;
   int* head = reinterpret_cast<int*>(smem + (size_t)2 * warps * L);  // merge cursors [warps]
   const int total = *n_flagged;
+  // more rows than the caller is willing to scan exhaustively (N*D fp64 FMAs each): leave them with their
+  // candidate-list result; the caller sees the count and re-runs the candidate pass with a tighter engine
+  if (limit >= 0 && (int64_t)total > limit) return;
   for (int f = blockIdx.x; f < total; f += gridDim.x) {
     const int64_t gid = flagged[f];
     const int64_t b = gid / n_rows, r = gid - b * n_rows;
@@ -493,7 +496,7 @@ int launch_knn_simt(const float* Yq, const float* Yall, int64_t batch, int64_t n
 int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t row0,
                    int64_t N, int D, const int32_t* cand_idx, const float* cand_sim, int kc, int k,
                    float eps, int32_t* top_idx, float* top_sim, float* gap, int64_t* flagged,
-                   int* n_flagged, cudaStream_t st) {
+                   int* n_flagged, cudaStream_t st, int64_t exhaustive_limit) {
   const int warps = 8;
   const size_t smem = (size_t)warps * kc * (sizeof(float) + sizeof(int));
   dim3 grid((unsigned)((n_rows + warps - 1) / warps), (unsigned)batch);
@@ -520,7 +523,8 @@ int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_
     const int64_t cap = 2 * (int64_t)sm_count();
     if (blocks > cap) blocks = cap;
     knn_exact_rows_kernel<<<(unsigned)blocks, warps * 32, sm2, st>>>(Yq, Yall, n_rows, row0, N, D, k, flagged,
-                                                                    n_flagged, top_idx, top_sim, gap);
+                                                                    n_flagged, top_idx, top_sim, gap,
+                                                                    exhaustive_limit);
     OSC_LAUNCH_CHECK("knn_exact_rows_kernel");
   }
   return OSC_OK;
