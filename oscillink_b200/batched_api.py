@@ -128,14 +128,38 @@ class BatchedLattices:
         need = C.c_size_t(0)
         _cabi.check(lib.osc_knn_rescore_workspace(B, N, C.byref(need)))
         rws = self._workspace(need.value)
-        phase("knn_rescore", lambda: lib.osc_knn_rescore_checked(
+        # single-product engines: the exhaustive path is bounded on the device (no host sync here); if the
+        # bound was exceeded (clustered / near-duplicate anchors) `_verify_build` rebuilds with 3xTF32
+        single = eng in (_cabi.KNN_TC1, _cabi.KNN_TCH)
+        self._exh_limit = int(lib.osc_knn_exhaustive_limit(rows)) if single else -1
+        self._build_verified = not single
+        phase("knn_rescore", lambda: lib.osc_knn_rescore_guarded(
             Yn.data_ptr(), Yn.data_ptr(), B, N, 0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
-            eps, top_idx.data_ptr(), top_sim.data_ptr(), self.gap.data_ptr(),
+            eps, self._exh_limit, top_idx.data_ptr(), top_sim.data_ptr(), self.gap.data_ptr(),
             self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st))
         phase("graph_assemble", lambda: lib.osc_graph_assemble(
             top_idx.data_ptr(), top_sim.data_ptr(), B, N, k, self.row_cap_val, self.nbr.data_ptr(),
             self.A.data_ptr(), self.W.data_ptr(), self.deg.data_ptr(), self.sqrt_deg.data_ptr(),
             self.nnz.data_ptr(), scratch.data_ptr(), st))
+
+    def build_exceeded(self) -> bool:
+        """True if the single-product kNN engine flagged more rows than the exhaustive path is allowed to
+        take (synchronises on first call): the graph then came from unproven candidate lists and must be
+        rebuilt with the 3xTF32 engine -- `_verify_build` does it."""
+        if getattr(self, "_build_verified", True):
+            return False
+        self._build_verified = True
+        return int(self.n_exhaustive.item()) > self._exh_limit >= 0
+
+    def _verify_build(self) -> bool:
+        if not self.build_exceeded():
+            return False
+        was = getattr(self, "engine_used", "?")
+        self._engine = _cabi.KNN_TC
+        self._ws = None
+        self._build()
+        self.engine_used = f"{self.engine_used} (fallback from {was})"
+        return True
 
     def phase_ms(self) -> dict:
         """Device time of every recorded phase (synchronises)."""
@@ -175,6 +199,8 @@ class BatchedLattices:
         if not self.supported():
             raise _cabi.OscillinkNativeError(
                 "batched kernel does not cover this shape; use OscillinkLattice per lattice")
+        if strict:
+            self._verify_build()  # (strict=False callers get the same check from resolve_flagged)
         B, dev = self.B, self._dev
         U_in = self.U
         U_out = torch.empty_like(self.Y)
@@ -216,6 +242,14 @@ class BatchedLattices:
     def resolve_flagged(self, out: dict[str, Any]) -> int:
         """Synchronise and settle every lattice flagged `unresolved` with the HBM-resident PCG
         (csrc/pcg.cu: global stop test every iteration).  Returns how many were redone."""
+        if self._verify_build():  # the graph itself had to be rebuilt: settle the whole batch again
+            a = self._last_call
+            self.U = self._U_prev
+            new = self.settle(dt=a["dt"], max_iters=a["max_iters"], tol=a["tol"], receipt=a["receipt"],
+                              ustar_tol=a["ustar_tol"], ustar_max_iters=a["ustar_max_iters"],
+                              keep_ustar=self.Ustar is not None, strict=True)
+            out.update(new)
+            return self.B
         flagged = torch.nonzero(out["unresolved"] & 1).flatten().tolist()
         if not flagged:
             return 0
@@ -321,7 +355,8 @@ def settle_host_batch(Y_host: torch.Tensor, psi_host: torch.Tensor, kneighbors: 
     # flagged lattices (pathological, see BatchedLattices.settle): redo with the global-test PCG.
     # bufY has been reused by then, so the chunk is fetched again from the host copy.
     for bl, out, lo, hi in pending:
-        if bool((out["unresolved"] & 1).any()):
+        if bl.build_exceeded() or bool((out["unresolved"] & 1).any()):
+            bl._build_verified = False  # (let resolve_flagged see the exceeded build again)
             bl.Y = Y_host[lo:hi].to(dev)
             bl.psi = psi_host[lo:hi].to(dev)
             bl.resolve_flagged(out)

@@ -58,16 +58,41 @@ __device__ __forceinline__ float block_total_cu(const float4* red, int lane) {
 // sum_t W_t v[nbr_t] for one row whose graph entries (byte offsets, weights) sit in registers
 template <int KQ>
 __device__ __forceinline__ V4 gather_regs(const float4* src, const ushort4 (&j)[KQ], const float4 (&w)[KQ]) {
-  V4 acc = v4_zero();
   const char* pb = reinterpret_cast<const char*>(src);
+  // all of the row's loads are issued before the first FMA consumes one (the loads are independent; written
+  // as `acc = fma(w, lds(...), acc)` the compiler keeps ONE load in flight per warp)
+  V4 v[4 * KQ];
 #pragma unroll
   for (int c = 0; c < KQ; ++c) {
-    acc = v4_fma_s(w[c].x, lds_v4(pb + j[c].x), acc);
-    acc = v4_fma_s(w[c].y, lds_v4(pb + j[c].y), acc);
-    acc = v4_fma_s(w[c].z, lds_v4(pb + j[c].z), acc);
-    acc = v4_fma_s(w[c].w, lds_v4(pb + j[c].w), acc);
+    v[4 * c + 0] = lds_v4(pb + j[c].x);
+    v[4 * c + 1] = lds_v4(pb + j[c].y);
+    v[4 * c + 2] = lds_v4(pb + j[c].z);
+    v[4 * c + 3] = lds_v4(pb + j[c].w);
+  }
+  V4 acc = v4_zero();
+#pragma unroll
+  for (int c = 0; c < KQ; ++c) {
+    acc = v4_fma_s(w[c].x, v[4 * c + 0], acc);
+    acc = v4_fma_s(w[c].y, v[4 * c + 1], acc);
+    acc = v4_fma_s(w[c].z, v[4 * c + 2], acc);
+    acc = v4_fma_s(w[c].w, v[4 * c + 3], acc);
   }
   return acc;
+}
+
+// the same for a graph image staged in shared memory (slot-major [c][row]): index/weight loads first,
+// then every p load of the row, then the FMAs
+template <int KQ>
+__device__ __forceinline__ V4 gather_smem(const float4* src, const ushort4* nbr_s, const float4* w_s, int row,
+                                          int stride) {
+  ushort4 j[KQ];
+  float4 w[KQ];
+#pragma unroll
+  for (int c = 0; c < KQ; ++c) {
+    j[c] = nbr_s[c * stride + row];
+    w[c] = w_s[c * stride + row];
+  }
+  return gather_regs<KQ>(src, j, w);
 }
 
 template <int TPT, int KQ, int T, bool GREG>
@@ -80,6 +105,8 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   __shared__ __align__(16) float4 y_static[Np];  // the slab's 4 columns of Y, prefetched with cp.async
   __shared__ __align__(16) float4 redA[RED_F4];  // p.Ap / deltaH partials (slots >= nw stay zero)
   __shared__ __align__(16) float4 redB[RED_F4];  // r.r partials
+  __shared__ __align__(16) float sc[8 * 4];      // broadcast CG scalars published by warp 0 (see the loop)
+  __shared__ int sflag[2];                       // stop verdicts {settle, stationary} of this iteration
   const int N = P.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* w_s = reinterpret_cast<float4*>(smem_raw);                  // [KQ][Np]   (GREG: unused)
@@ -196,7 +223,7 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
         if (wact[m]) {
           const float4 y = y_static[row];
           const V4 g0 = GREG ? gather_regs<KQ>(y_static, jj[GREG ? m : 0], ww[GREG ? m : 0])
-                             : gather_row<KQ>(y_static, nbr_s, w_s, row, Np, KQ);
+                             : gather_smem<KQ>(y_static, nbr_s, w_s, row, Np);
           // lattice.py:184,256 (same rounding order); pad rows carry zeros
           const float4 rhs = act[m]
                                  ? make_float4(__fadd_rn(__fmul_rn(P.lamG, y.x), __fmul_rn(P.lamQ, psi4.x)),
@@ -216,79 +243,113 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
       }
       warp_reduce4(to_f4(part), redB + warp, lane);
       __syncthreads();  // r0 visible, r0.r0 partials visible
-      float rr = block_total_cu<nw>(redB, lane);  // column lane & 3
-      float rz = rr * im;
-      // per-column shift state (lane's column)
-      float zeta = 1.f, zeta_p = 1.f, a_prev = 1.f, b_prev = 0.f, beta = 0.f;
+      // The CG scalars are the same for every warp.  WARP 0 ALONE evaluates them (per column: lane & 3) and
+      // publishes the broadcast operands through shared memory; the other warps wait on a barrier and read
+      // them back with broadcast LDS.128.  (Every warp doing the scalar algebra itself cost ~250 of the
+      // ~310 non-gather instructions per warp and iteration -- more issue slots than the gather pass.)
+      float rr = 0.f, rz = 0.f;
+      if (warp == 0) {
+        rr = block_total_cu<nw>(redB, lane);  // column lane & 3
+        rz = rr * im;
+      }
+      // per-column shift state (warp 0, lane's column)
+      float zeta = 1.f, zeta_p = 1.f, a_prev = 1.f, b_prev = 0.f;
       bool fs = false, fu = false, ru_in_scr = false;
       int Ts = 0, Tu = 0;
       float rrs_rec = 0.f, rru_rec = 0.f;
+      V4 BETA = v4_zero();  // beta_{k-1} for the G recurrence
       int k = 0;
       while (true) {
         ++k;
         // ---- gather r_k ; G = im * gather + beta G ; p.Ap
-        const V4 BETA = to_v4(bcast4(beta));
         part = v4_zero();
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
           if (wact[m]) {
             const V4 g = GREG ? gather_regs<KQ>(r_static, jj[GREG ? m : 0], ww[GREG ? m : 0])
-                              : gather_row<KQ>(r_static, nbr_s, w_s, tid + T * m, Np, KQ);
+                              : gather_smem<KQ>(r_static, nbr_s, w_s, tid + T * m, Np);
             G[m] = v4_fma(IM, g, v4_mul(BETA, G[m]));
             part = v4_fma(Pv[m], combine_row(Pv[m], G[m], diag, noffc), part);
           }
         }
         warp_reduce4(to_f4(part), redA + warp, lane);
-        __syncthreads();  // B1: every gather of r_k is done
-        const float pap = block_total_cu<nw>(redA, lane);
-        // solver.py:23.  The step lengths of the shift recurrences use the fast division: 2 ulp on alpha
-        // moves the iterates by ~1e-7 relative, far inside the 1e-5 parity bound, and is not on any knife
-        // edge (the stop tests below compare reduced norms, not quotients)
-        const float alpha = __fdividef(rz, pap + 1e-18f);
-        const float a = alpha * im;  // plain-CG step length
-        const float den = a * b_prev * (zeta_p - zeta) + zeta_p * a_prev * (1.0f + sigma * a);
-        const float zn = den != 0.f ? __fdividef(zeta * zeta_p * a_prev, den) : zeta;
-        const float ratio = zeta != 0.f ? __fdividef(zn, zeta) : 0.f;
-        const float4 al4 = bcast4(alpha);
-        const V4 AL = to_v4(al4);
-        const V4 NAL = to_v4(make_float4(-al4.x, -al4.y, -al4.z, -al4.w));
-        const V4 AS = to_v4(bcast4(fs ? 0.f : a * ratio));
-        const V4 AU = fu ? v4_zero() : AL;
-        // ---- x_u += alpha p ; x_s += a^s p^s ; r -= alpha A p ; publish r ; r.r
-        part = v4_zero();
+        __syncthreads();  // B1: every gather of r_k is done, p.Ap partials visible
+        float a = 0.f, zn = 1.f, ratio = 0.f;
+        if (warp == 0) {
+          const float pap = block_total_cu<nw>(redA, lane);
+          // solver.py:23.  The step lengths of the shift recurrences use the fast division: 2 ulp on alpha
+          // moves the iterates by ~1e-7 relative, far inside the 1e-5 parity bound, and is not on any knife
+          // edge (the stop tests below compare reduced norms, not quotients)
+          const float alpha = __fdividef(rz, pap + 1e-18f);
+          a = alpha * im;  // plain-CG step length
+          const float den = a * b_prev * (zeta_p - zeta) + zeta_p * a_prev * (1.0f + sigma * a);
+          zn = den != 0.f ? __fdividef(zeta * zeta_p * a_prev, den) : zeta;
+          ratio = zeta != 0.f ? __fdividef(zn, zeta) : 0.f;
+          if (lane < 4) {
+            sc[0 * 4 + lane] = alpha;
+            sc[1 * 4 + lane] = -alpha;
+            sc[2 * 4 + lane] = fs ? 0.f : a * ratio;
+            sc[3 * 4 + lane] = fu ? 0.f : alpha;
+          }
+        }
+        __syncthreads();  // B1b: step lengths published
+        {
+          const V4 NAL = lds_v4(sc + 4), AS = lds_v4(sc + 8), AU = lds_v4(sc + 12);
+          // ---- x_u += alpha p ; x_s += a^s p^s ; r -= alpha A p ; publish r ; r.r
+          part = v4_zero();
 #pragma unroll
-        for (int m = 0; m < TPT; ++m) {
-          if (wact[m]) {
-            const V4 ap = combine_row(Pv[m], G[m], diag, noffc);
-            Xu[m] = v4_fma(Pv[m], AU, Xu[m]);
-            Xs[m] = v4_fma(Ps[m], AS, Xs[m]);
-            R[m] = v4_fma(ap, NAL, R[m]);
-            part = v4_fma(R[m], R[m], part);
-            sts_v4(r_static + tid + T * m, R[m]);
+          for (int m = 0; m < TPT; ++m) {
+            if (wact[m]) {
+              const V4 ap = combine_row(Pv[m], G[m], diag, noffc);
+              Xu[m] = v4_fma(Pv[m], AU, Xu[m]);
+              Xs[m] = v4_fma(Ps[m], AS, Xs[m]);
+              R[m] = v4_fma(ap, NAL, R[m]);
+              part = v4_fma(R[m], R[m], part);
+              sts_v4(r_static + tid + T * m, R[m]);
+            }
           }
         }
         warp_reduce4(to_f4(part), redB + warp, lane);
         __syncthreads();  // B2: r_{k+1} visible, r.r partials visible
-        const float rr_new = block_total_cu<nw>(redB, lane);
-        const float rzn = rr_new * im;
-        beta = __fdividef(rzn, rz + 1e-18f);  // solver.py:34
-        const float bs = beta * ratio * ratio;
-        // stop tests (solver.py:29-31): stationary on ||r||, settle on ||dt zeta r||, max over the slab's
-        // columns.  thr2_* is the largest fp32 x with (double)sqrtf(x) <= tol, so `m <= thr2` is exactly the
-        // reference's `float32 norm <= tol` without a square root or an fp64 compare on the critical path.
-        const float zs = P.dt * zn;
-        float mu = rr_new, ms = zs * zs * rr_new;
-        mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 1));
-        ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 1));
-        mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 2));
-        ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
-        // identical in every thread (same summation order) -> uniform branches
-        const bool stop_s = !fs && (Fs > 0 ? (k >= Fs) : (ms <= P.thr2_settle || k >= P.max_iters_settle));
-        const bool stop_u = !fu && (Fu > 0 ? (k >= Fu) : (mu <= P.thr2_ustar || k >= P.max_iters_ustar));
+        if (warp == 0) {
+          const float rr_new = block_total_cu<nw>(redB, lane);
+          const float rzn = rr_new * im;
+          const float beta = __fdividef(rzn, rz + 1e-18f);  // solver.py:34
+          const float bs = beta * ratio * ratio;
+          // stop tests (solver.py:29-31): stationary on ||r||, settle on ||dt zeta r||, max over the slab's
+          // columns.  thr2_* is the largest fp32 x with (double)sqrtf(x) <= tol, so `m <= thr2` is exactly the
+          // reference's `float32 norm <= tol` without a square root or an fp64 compare on the critical path.
+          const float zs = P.dt * zn;
+          float mu = rr_new, ms = zs * zs * rr_new;
+          mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 1));
+          ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 1));
+          mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 2));
+          ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
+          const bool st_s = !fs && (Fs > 0 ? (k >= Fs) : (ms <= P.thr2_settle || k >= P.max_iters_settle));
+          const bool st_u = !fu && (Fu > 0 ? (k >= Fu) : (mu <= P.thr2_ustar || k >= P.max_iters_ustar));
+          if (lane < 4) {
+            sc[4 * 4 + lane] = beta;
+            sc[5 * 4 + lane] = zn;
+            sc[6 * 4 + lane] = bs;
+          }
+          if (lane == 0) {
+            sflag[0] = st_s ? 1 : 0;
+            sflag[1] = st_u ? 1 : 0;
+          }
+          if (st_s) rrs_rec = ms;
+          if (st_u) rru_rec = mu;
+          zeta_p = zeta;
+          zeta = zn;
+          a_prev = a;
+          b_prev = beta;
+          rz = rzn;
+        }
+        __syncthreads();  // B2b: beta / zeta / verdicts published
+        const bool stop_s = sflag[0] != 0, stop_u = sflag[1] != 0;  // uniform
+        const V4 ZN = lds_v4(sc + 20);
         if (stop_s) {
           // U+ out; M U+ = RHS + (Y - U+)/dt - zeta r  (the settle system's own residual is dt zeta r):
           // the dead p^s registers take t1 = (Y - U+)/dt - zeta r for the deltaH identity
-          const V4 ZN = to_v4(bcast4(zn));
           const V4 SG = v4_bc(sigma);
 #pragma unroll
           for (int m = 0; m < TPT; ++m) {
@@ -299,7 +360,6 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
           }
           fs = true;
           Ts = k;
-          rrs_rec = ms;
           y_next();
         }
         if (stop_u) {
@@ -316,23 +376,16 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
           }
           fu = true;
           Tu = k;
-          rru_rec = mu;
         }
         if (fs && fu) break;
         // ---- p = im r + beta p ; p^s = zeta r + b^s p^s
-        const V4 BT = to_v4(bcast4(beta));
-        const V4 ZN = to_v4(bcast4(zn));
-        const V4 BS = to_v4(bcast4(bs));
+        BETA = lds_v4(sc + 16);
+        const V4 BS = lds_v4(sc + 24);
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
-          Pv[m] = v4_fma(Pv[m], BT, v4_mul(IM, R[m]));
+          Pv[m] = v4_fma(Pv[m], BETA, v4_mul(IM, R[m]));
           if (!fs) Ps[m] = v4_fma(Ps[m], BS, v4_mul(ZN, R[m]));
         }
-        zeta_p = zeta;
-        zeta = zn;
-        a_prev = a;
-        b_prev = beta;
-        rz = rzn;
       }
       if (tid == 0) {
         P.rec[(b * 2 + 0) * P.G + s] = make_int2(Ts, __float_as_int(rrs_rec));

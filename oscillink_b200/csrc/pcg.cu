@@ -217,24 +217,32 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
           for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
         }
       }
-      if (t + 4 <= n) {
-        float x[4][VEC];
+      // remainder (1..7 neighbours): ONE masked batch instead of a 4-batch plus single dependent loads --
+      // at k = 10 a row with 9 or 10 neighbours used to take two or three DRAM round trips, now two.
+      // Masked lanes re-read the row's own segment (just fetched, an L1 hit) with weight 0.
+      if (t < n) {
+        const float* own_p = (vv.local_ids ? vv.all + i * dm.D : row_ptr(vv, gi, dm.D)) + co;
+        if (n - t > 4) {
+          float x[8][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) ldv<VEC>(nb[t + u] + co, x[u]);
+          for (int u = 0; u < 8; ++u) ldv<VEC>(t + u < n ? nb[t + u] + co : own_p, x[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float w = wt[t + u];
+          for (int u = 0; u < 8; ++u) {
+            const float w = t + u < n ? wt[t + u] : 0.f;
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+            for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+          }
+        } else {
+          float x[4][VEC];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ldv<VEC>(t + u < n ? nb[t + u] + co : own_p, x[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float w = t + u < n ? wt[t + u] : 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+          }
         }
-        t += 4;
-      }
-      for (; t < n; ++t) {
-        float x[VEC];
-        ldv<VEC>(nb[t] + co, x);
-        const float w = wt[t];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[v], s[v]);
       }
       const float b = gates ? gates[i] : 1.0f;
       const float dg = op_diag(c, b);
@@ -503,6 +511,14 @@ static size_t spmm_smem_bytes(const dim3& blk, int vec, int k, int rch) {
 // rows per staged chunk: SPMM_RCH when that fits the 48 KB default, else the largest power of two that
 // does; ELL rows too wide even for one row per chunk use the opt-in limit.  0 = does not fit at all.
 static int spmm_chunk_rows(const dim3& blk, int vec, int k) {
+  // Narrow rows (column slabs of a sharded lattice: D/G floats) put many row lanes in a block: a chunk is
+  // then a whole number of rows per lane and at least 4 of them, so that the two barriers per chunk are
+  // amortised and no lane idles in the last pass (D = 48: 21 lanes, 84 rows per chunk instead of 32, where
+  // the second pass ran 11 of 21 lanes; measured 5.6 ms -> see DESIGN.md at N = 10M).
+  int want = SPMM_RCH;
+  const int ry = (int)blk.y;
+  if (ry > 2) want = ry * (ry > 8 ? 4 : (SPMM_RCH + ry - 1) / ry);
+  if (spmm_smem_bytes(blk, vec, k, want) <= 48 * 1024) return want;
   for (int rch = SPMM_RCH; rch >= 1; rch >>= 1)
     if (spmm_smem_bytes(blk, vec, k, rch) <= 48 * 1024) return rch;
   return spmm_smem_bytes(blk, vec, k, 1) <= kSpmmSmemMax ? 1 : 0;

@@ -507,25 +507,41 @@ class ShardedLattice:
             else:
                 cabi.check(lib.osc_normalize_rows(Y_all.data_ptr(), N, D, Yn.data_ptr(), P(hi), P(lo), st))
             nl, r0 = self.n_local, self.row0
-            cand_idx = torch.empty((max(nl, 1), kc), dtype=torch.int32, device=dev)
-            cand_sim = torch.empty((max(nl, 1), kc), dtype=torch.float32, device=dev)
             top_idx = torch.full((max(nl, 1), k), -1, dtype=torch.int32, device=dev)
             top_sim = torch.zeros((max(nl, 1), k), dtype=torch.float32, device=dev)
             gap = torch.empty(max(nl, 1), dtype=torch.float32, device=dev)
             if nl > 0:
                 q = lambda t: None if t is None else t.data_ptr() + r0 * D * t.element_size()  # noqa: E731
-                cabi.check(lib.osc_knn_candidates(
-                    q(Yn), Yn.data_ptr(), q(hi), q(lo), P(hi), P(lo), 1, nl, r0, N, D, kc,
-                    eng, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st), "osc_knn_candidates")
                 self.n_exhaustive = torch.zeros(1, dtype=torch.int32, device=dev)
                 need = C.c_size_t(0)
                 cabi.check(lib.osc_knn_rescore_workspace(1, nl, C.byref(need)))
                 rws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
-                cabi.check(lib.osc_knn_rescore_checked(
-                    q(Yn), Yn.data_ptr(), 1, nl, r0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
-                    eps, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
-                    self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st),
-                    "osc_knn_rescore_checked")
+
+                def run(eng, kc, eps, hi, lo, limit):
+                    cand_idx = torch.empty((nl, kc), dtype=torch.int32, device=dev)
+                    cand_sim = torch.empty((nl, kc), dtype=torch.float32, device=dev)
+                    cabi.check(lib.osc_knn_candidates(
+                        q(Yn), Yn.data_ptr(), q(hi), q(lo), P(hi), P(lo), 1, nl, r0, N, D, kc,
+                        eng, cand_idx.data_ptr(), cand_sim.data_ptr(), None, 0, st), "osc_knn_candidates")
+                    cabi.check(lib.osc_knn_rescore_guarded(
+                        q(Yn), Yn.data_ptr(), 1, nl, r0, N, D, cand_idx.data_ptr(), cand_sim.data_ptr(), kc, k,
+                        eps, limit, top_idx.data_ptr(), top_sim.data_ptr(), gap.data_ptr(),
+                        self.n_exhaustive.data_ptr(), rws.data_ptr(), rws.numel(), st),
+                        "osc_knn_rescore_guarded")
+
+                # single-product engines: bounded exhaustive path, hand-over to 3xTF32 if too many rows of this
+                # rank cannot be proven complete (clustered / near-duplicate anchors) -- rank-local decision
+                single = eng in (cabi.KNN_TC1, cabi.KNN_TCH)
+                limit = int(lib.osc_knn_exhaustive_limit(nl)) if single else -1
+                run(eng, kc, eps, hi, lo, limit)
+                if single and int(self.n_exhaustive.item()) > limit:
+                    e3, kc3, eps3 = cabi.knn_plan(nl, N, D, k, cabi.KNN_TC)
+                    del hi, lo
+                    hi, lo = torch.empty_like(Y_all), torch.empty_like(Y_all)
+                    cabi.check(lib.osc_normalize_rows(Y_all.data_ptr(), N, D, Yn.data_ptr(), hi.data_ptr(),
+                                                      lo.data_ptr(), st))
+                    run(e3, kc3, eps3, hi, lo, -1)
+                    self.engine_used = cabi.ENGINE_NAMES[e3] + " (fallback from " + self.engine_used + ")"
             self.gap_local = gap[:nl]
             top_idx_all = gather_rows(top_idx[:nl], N, self.group).contiguous()
             top_sim_all = gather_rows(top_sim[:nl], N, self.group).contiguous()

@@ -49,7 +49,7 @@ def test_batched_matches_oracle(B, N, D, k):
         assert np.linalg.norm(Us[b] - ous) / np.linalg.norm(ous) < TOL
         assert rel(float(out["deltaH"][b].item()), o.delta_h(ous)) < TOL
         if int(out["iters"][b].item()) == st["iters"]:
-            assert rel(float(out["res"][b].item()), st["res"]) < 1e-3
+            assert rel(float(out["res"][b].item()), st["res"]) < 1e-4
 
 
 def test_batched_lattice0_is_config2_golden():
@@ -64,7 +64,7 @@ def test_batched_lattice0_is_config2_golden():
     assert np.array_equal(bl.nbr[0].cpu().numpy(), z["nbr"])
     assert int(out["iters"][0].item()) == g["settle"]["iters"]
     assert int(out["ustar_iters"][0].item()) == g["ustar"]["iters"]
-    assert rel(float(out["res"][0].item()), g["settle"]["res"]) < 1e-3
+    assert rel(float(out["res"][0].item()), g["settle"]["res"]) < 1e-4
     assert rel(float(out["deltaH"][0].item()), g["deltaH"]) < TOL
     assert int(bl.nnz[0].item()) == g["nnz"]
 
@@ -125,7 +125,7 @@ def test_batched_uneven_slabs_are_rerun_to_lattice_count():
         ous, it, res = o.stationary()
         assert int(out["iters"][b].item()) == st["iters"]
         assert int(out["ustar_iters"][b].item()) == it
-        assert rel(float(out["res"][b].item()), st["res"]) < 1e-3
+        assert rel(float(out["res"][b].item()), st["res"]) < 1e-4
         assert np.linalg.norm(U[b] - o.U) / np.linalg.norm(o.U) < TOL
         # the quiet columns must carry exactly the lattice's iteration count as well
         assert np.linalg.norm(U[b][:, :8] - o.U[:, :8]) / np.linalg.norm(o.U[:, :8]) < 1e-4
@@ -204,8 +204,8 @@ def test_multishift_matches_two_solve_oracle(kw):
         ous, it, res = o.stationary(tol=kw["ustar_tol"], max_iters=kw.get("ustar_max_iters", 64))
         assert int(out["iters"][b].item()) == st["iters"]
         assert int(out["ustar_iters"][b].item()) == it
-        assert rel(float(out["res"][b].item()), st["res"]) < 2e-3
-        assert rel(float(out["ustar_res"][b].item()), res) < 2e-3
+        assert rel(float(out["res"][b].item()), st["res"]) < 1e-4
+        assert rel(float(out["ustar_res"][b].item()), res) < 1e-4
         assert np.linalg.norm(U[b] - o.U) / np.linalg.norm(o.U) < TOL
         assert np.linalg.norm(Us[b] - ous) / np.linalg.norm(ous) < TOL
         assert rel(float(out["deltaH"][b].item()), o.delta_h(ous)) < TOL
@@ -235,7 +235,7 @@ def test_multishift_equals_two_solve_kernel(N, D, k, monkeypatch):
     assert np.linalg.norm(a[0] - b[0]) / np.linalg.norm(b[0]) < 2e-6
     assert np.linalg.norm(a[1] - b[1]) / np.linalg.norm(b[1]) < 2e-6
     assert np.allclose(a[4], b[4], rtol=1e-5)
-    assert np.allclose(a[5], b[5], rtol=2e-3)
+    assert np.allclose(a[5], b[5], rtol=1e-4)
 
 
 def test_multishift_uneven_slabs_forced_counts(monkeypatch):

@@ -7,6 +7,14 @@ artefacts, (c) the sparse oracle on the same seeded inputs.
 Tolerances (BASELINE.json north_star): neighbour index sets bit-exact; U, U*, deltaH within
 1e-5 relative (norm-wise for arrays); CG iteration counts within +-1; residual
 scalars compared at equal iteration count.
+
+Every other receipt quantity (coh_drop / anchor / query sums, null-point z and residual, bundle score and
+alignment, the residual scalars) is held to max(1e-5, 10 x the reference's OWN noise floor), measured by
+oracle/noise_floor.py (tests/golden/noise_floor.json): the unmodified reference run on row-permuted copies
+of the same case, i.e. only the order in which NumPy/OpenBLAS sums changes.  The floors are 1e-7 .. 8e-7 for
+the receipt terms and 4e-6 for the residual scalars (a difference of numbers five orders of magnitude
+larger); the deviations of the CUDA path measured on B200 are 1.2e-7 .. 1.2e-6 and 2.5e-6
+(profiles/r02_parity_margins.json, tools/dev_parity_margins.py).
 """
 import numpy as np
 import pytest
@@ -17,6 +25,23 @@ from tests.helpers import artefacts, load_golden, rel
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+
+
+def _floor_tol(key):
+    """max(1e-5, 10 x the reference's own permutation noise floor for `key`)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "noise_floor.json")) as f:
+        fl = json.load(f)
+    worst = max(v[key] for name, v in fl.items() if not name.startswith("_"))
+    return max(TOL, 10.0 * worst)
+
+
+TOL_RES = _floor_tol("settle_res")          # residual scalars: 4.0e-5
+TOL_NULL = max(_floor_tol("null_z"), _floor_tol("null_residual"))   # 1e-5
+TOL_COH = _floor_tol("coh_drop_sum")        # 1e-5
+TOL_BUNDLE = max(_floor_tol("bundle_score"), _floor_tol("bundle_align"))  # 1e-5
 
 
 @pytest.fixture(scope="module")
@@ -61,7 +86,7 @@ def test_lattice_matches_reference_golden(api, name):
     st = lat.settle(**c["settle_kw"])
     assert abs(st["iters"] - g["settle"]["iters"]) <= 1
     if st["iters"] == g["settle"]["iters"] and g["settle"]["res"] > 1e-6:
-        assert rel(st["res"], g["settle"]["res"]) < 1e-3
+        assert rel(st["res"], g["settle"]["res"]) < TOL_RES
     U1 = lat.U.copy()
     if c["second_settle"]:
         st2 = lat.settle(**c["second_settle"])
@@ -94,15 +119,15 @@ def test_lattice_matches_reference_golden(api, name):
         lat.set_receipt_detail("full")
         rf = lat.receipt()
         gf = g["full"]
-        assert rel(rf["coh_drop_sum"], gf["coh_drop_sum"]) < 5e-5 or abs(
-            rf["coh_drop_sum"] - gf["coh_drop_sum"]) < 1e-4
+        assert rel(rf["coh_drop_sum"], gf["coh_drop_sum"]) < TOL_COH or abs(
+            rf["coh_drop_sum"] - gf["coh_drop_sum"]) < 1e-6
         assert rel(rf["anchor_pen_sum"], gf["anchor_pen_sum"]) < TOL
         assert rel(rf["query_term_sum"], gf["query_term_sum"]) < TOL
         assert len(rf["null_points"]) == gf["n_null"]
         assert [e["edge"] for e in rf["null_points"]] == z["null_edges"].tolist()
         if gf["n_null"]:
-            np.testing.assert_allclose([e["z"] for e in rf["null_points"]], z["null_z"], rtol=1e-4)
-            np.testing.assert_allclose([e["residual"] for e in rf["null_points"]], z["null_R"], rtol=1e-4)
+            np.testing.assert_allclose([e["z"] for e in rf["null_points"]], z["null_z"], rtol=TOL_NULL)
+            np.testing.assert_allclose([e["residual"] for e in rf["null_points"]], z["null_R"], rtol=TOL_NULL)
 
 
 @pytest.mark.parametrize("name", sorted(artefacts()))
@@ -115,14 +140,14 @@ def test_lattice_matches_reference_artefacts(api, name):
     lat.set_receipt_detail("full" if "null_points" in ref else "light")
     rec = lat.receipt()
     assert rec["meta"]["ustar_iters"] == ref["ustar_iters"]
-    assert rel(rec["meta"]["ustar_res"], ref["ustar_res"]) < 1e-3
+    assert rel(rec["meta"]["ustar_res"], ref["ustar_res"]) < TOL_RES
     assert rel(rec["deltaH_total"], ref["deltaH"]) < TOL
     if "null_points" in ref:
         assert len(rec["null_points"]) == ref["null_points"]
         first = rec["null_points"][0]
         assert first["edge"] == ref["sample_null"]["edge"]
-        assert rel(first["z"], ref["sample_null"]["z"]) < 1e-4
-        assert rel(first["residual"], ref["sample_null"]["residual"]) < 1e-4
+        assert rel(first["z"], ref["sample_null"]["z"]) < TOL_NULL
+        assert rel(first["residual"], ref["sample_null"]["residual"]) < TOL_NULL
 
 
 @pytest.mark.parametrize("name", ["config2_1200", "gates_300", "perf_400", "zero_row_40"])
@@ -421,7 +446,7 @@ def test_packed_key_lists_handle_negative_scores_and_the_column_limit(N):
 
 @pytest.mark.parametrize("name", ["quickstart_120", "readme_80", "config2_1200", "gates_300"])
 def test_bundle_matches_reference(api, name):
-    """f1: bundle() ids identical, scores / alignments within 1e-4 (z-scores amplify fp32 noise)."""
+    """f1: bundle() ids identical, scores / alignments within max(1e-5, 10 x the reference's own floor)."""
     g, _ = load_golden(name)
     c = cases.build(name)
     lat = _make(api, c)
@@ -430,8 +455,8 @@ def test_bundle_matches_reference(api, name):
         lat.settle(**c["second_settle"])
     out = lat.bundle(k=c["bundle_k"])
     assert [e["id"] for e in out] == [e["id"] for e in g["bundle"]]
-    np.testing.assert_allclose([e["score"] for e in out], [e["score"] for e in g["bundle"]], rtol=2e-4, atol=2e-5)
-    np.testing.assert_allclose([e["align"] for e in out], [e["align"] for e in g["bundle"]], rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose([e["score"] for e in out], [e["score"] for e in g["bundle"]], rtol=TOL_BUNDLE, atol=1e-7)
+    np.testing.assert_allclose([e["align"] for e in out], [e["align"] for e in g["bundle"]], rtol=TOL_BUNDLE, atol=1e-7)
     assert lat.bundle(k=0) == []
 
 
@@ -449,12 +474,12 @@ def test_chain_receipt_matches_reference(api, name):
     assert cr["verdict"] == ref["verdict"]
     assert cr["weakest_link"]["k"] == ref["weakest_link"]["k"]
     assert cr["weakest_link"]["edge"] == ref["weakest_link"]["edge"]
-    assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < 1e-4
-    assert abs(cr["coherence_gain"] - ref["coherence_gain"]) <= 1e-4 * max(1.0, abs(ref["coherence_gain"]))
+    assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < TOL_NULL
+    assert abs(cr["coherence_gain"] - ref["coherence_gain"]) <= TOL_NULL * max(1.0, abs(ref["coherence_gain"]))
     for a, b in zip(cr["edges"], ref["edges"]):
         assert a["edge"] == b["edge"]
         for key in ("z_struct", "z_path", "r_struct", "r_path"):
-            assert abs(a[key] - b[key]) <= 1e-4 * max(1.0, abs(b[key])), (key, a, b)
+            assert abs(a[key] - b[key]) <= TOL_NULL * max(1.0, abs(b[key])), (key, a, b)
 
 
 def test_perf_snapshot_weakest_link(api):
@@ -466,7 +491,7 @@ def test_perf_snapshot_weakest_link(api):
     cr = lat.chain_receipt(c["chain"])
     assert cr["verdict"] == ref["chain_verdict"]
     assert cr["weakest_link"]["edge"] == ref["weakest_link"]["edge"]
-    assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < 1e-4
+    assert rel(cr["weakest_link"]["zscore"], ref["weakest_link"]["zscore"]) < TOL_NULL
 
 
 # --------------------------------------------------------------------------- candidate-list completeness

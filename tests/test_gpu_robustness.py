@@ -142,3 +142,73 @@ def test_sparse_state_with_scattered_padding_is_compacted(api):
     bad["A_ell"] = {"nbr": np.where(nbr < 0, -2, nbr).tolist(), "val": val.tolist()}
     with pytest.raises(ValueError):
         api.OscillinkLattice.from_state(bad)
+
+
+def _clustered(N, D, n_clusters, sigma, seed):
+    rs = np.random.RandomState(seed)
+    centers = rs.randn(n_clusters, D).astype(np.float32)
+    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+    lab = rs.randint(0, n_clusters, size=N)
+    return (centers[lab] + sigma * rs.randn(N, D)).astype(np.float32)
+
+
+def test_clustered_anchors_hand_over_to_the_3xtf32_engine(api):
+    """64 tight clusters: almost every row has more than kc neighbours within the single-product engines'
+    error bound (1.25e-3), so their candidate lists cannot be proven complete.  The build must NOT send
+    those rows through the exhaustive kernel (N*D fp64 FMAs per row): it re-runs the candidate pass with the
+    3xTF32 engine, and the graph is still the canonical one."""
+    import time
+
+    import torch
+
+    from oracle.sparse import assemble, normalise_rows, topk_canonical
+    from oscillink_b200.sharded_api import ShardedLattice
+
+    N, D, k = 20000, 64, 10
+    Y = _clustered(N, D, 64, 0.01, seed=21)
+    idx, sim, gap = topk_canonical(normalise_rows(Y), k)
+    want = assemble(idx, sim, 1.0)[0].astype(np.int32)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    lat = api.OscillinkLattice(Y, kneighbors=k, deterministic_k=True)
+    torch.cuda.synchronize()
+    t_class = time.time() - t0
+    assert np.array_equal(lat._nbr.cpu().numpy(), want)
+    t0 = time.time()
+    sl = ShardedLattice(Y, N, kneighbors=k)
+    torch.cuda.synchronize()
+    t_sharded = time.time() - t0
+    assert np.array_equal(sl._nbr.cpu().numpy(), want)
+    assert "fallback" in sl.engine_used, sl.engine_used
+    # an exhaustive scan of every row would be N^2*D = 2.6e10 fp64 FMAs plus 20000 serial list merges
+    assert t_class < 5.0 and t_sharded < 5.0, (t_class, t_sharded)
+
+
+def test_clustered_batch_is_rebuilt_after_the_fact(api):
+    """BatchedLattices bounds the exhaustive path on the device (no host sync in the build) and rebuilds
+    with the 3xTF32 engine when the bound was exceeded: strict settle and the pipelined host call."""
+    import torch
+
+    from oracle.sparse import SparseLattice
+    from oscillink_b200 import BatchedLattices, settle_host_batch
+
+    B, N, D, k = 3, 1000, 32, 8
+    Y = np.stack([_clustered(N, D, 16, 0.01, seed=40 + b) for b in range(B)])
+    psi = np.stack([Y[b, :32].mean(axis=0) / (np.linalg.norm(Y[b, :32].mean(axis=0)) + 1e-12) for b in range(B)])
+    psi = psi.astype(np.float32)
+    bl = BatchedLattices(Y, kneighbors=k)
+    bl.set_query(psi)
+    out = bl.settle(receipt=True)
+    assert "fallback" in bl.engine_used, bl.engine_used
+    got = settle_host_batch(torch.from_numpy(Y).pin_memory(), torch.from_numpy(psi).pin_memory(), kneighbors=k,
+                            chunk=2).numpy()
+    for b in range(B):
+        o = SparseLattice(Y[b], k=k)
+        o.set_query(psi[b])
+        st = o.settle()
+        us, it, _ = o.stationary()
+        assert np.array_equal(bl.nbr[b].cpu().numpy(), o.nbr.astype(np.int32))
+        assert int(out["iters"][b].item()) == st["iters"] == int(got[b, 0])
+        assert int(out["ustar_iters"][b].item()) == it == int(got[b, 2])
+        assert rel(float(out["deltaH"][b].item()), o.delta_h(us)) < 1e-5
+        assert rel(float(got[b, 4]), o.delta_h(us)) < 1e-5
