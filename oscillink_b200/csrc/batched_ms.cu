@@ -102,14 +102,16 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   constexpr int nw = T >> 5;
   // both gather sources are STATIC shared memory: a gather is LDS.128 [u16 offset + constant]
   __shared__ __align__(16) float4 r_static[Np];  // r_k (the gathered vector)
-  __shared__ __align__(16) float4 y_static[Np];  // the slab's 4 columns of Y, prefetched with cp.async
   __shared__ __align__(16) float4 redA[RED_F4];  // p.Ap / deltaH partials (slots >= nw stay zero)
   __shared__ __align__(16) float4 redB[RED_F4];  // r.r partials
   __shared__ __align__(16) float sc[8 * 4];      // broadcast CG scalars published by warp 0 (see the loop)
   __shared__ int sflag[2];                       // stop verdicts {settle, stationary} of this iteration
   const int N = P.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float4* w_s = reinterpret_cast<float4*>(smem_raw);                  // [KQ][Np]   (GREG: unused)
+  // dynamic shared memory: two Y-slab buffers [2][Np] float4 (the 4 columns of Y of the current slab and,
+  // prefetched with cp.async while it iterates, of the next one), then the graph image (GREG: none)
+  float4* y_buf = reinterpret_cast<float4*>(smem_raw);
+  float4* w_s = y_buf + 2 * Np;                                        // [KQ][Np]
   ushort4* nbr_s = reinterpret_cast<ushort4*>(w_s + (size_t)Np * KQ);  // [KQ][Np]
   if (!GREG) {
     for (int e = tid; e < Np * KQ; e += T) {
@@ -119,7 +121,8 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   }
   for (int e = tid; e < Np; e += T) {
     r_static[e] = f4_zero();
-    y_static[e] = f4_zero();
+    y_buf[e] = f4_zero();
+    y_buf[Np + e] = f4_zero();
   }
   if (tid < RED_F4) {
     redA[tid] = f4_zero();
@@ -136,11 +139,13 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   const int64_t n_work = list_mode ? (int64_t)(*P.fix_count) : P.n_work;
   float4* scr = P.scratch + (size_t)blockIdx.x * 2 * N;  // r_{T_u} when the base system stops first (rare)
   bool y_ahead = false;
-  auto y_fetch = [&](int64_t fb, int fs) {
+  int y_sel = 0;  // which Y buffer holds the slab being processed
+  auto y_fetch = [&](int64_t fb, int fs, int sel) {
     const float* src = P.Y + fb * (int64_t)N * P.D + fs * SC;
+    float4* dst = y_buf + sel * Np;
 #pragma unroll
     for (int m = 0; m < TPT; ++m)
-      if (act[m]) cp_async16(y_static + tid + T * m, src + (int64_t)(tid + T * m) * P.D);
+      if (act[m]) cp_async16(dst + tid + T * m, src + (int64_t)(tid + T * m) * P.D);
     cp_async_commit();
   };
 
@@ -197,21 +202,23 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
     for (int s = s0; s < s1; ++s) {
       const int col = s * SC;
       const float4 psi4 = *reinterpret_cast<const float4*>(P.psi + b * P.D + col);
-      if (!y_ahead) y_fetch(b, s);
+      if (y_ahead) y_sel ^= 1;  // the slab prefetched during the previous one
+      else y_fetch(b, s, y_sel);
       cp_async_wait_all();
       y_ahead = false;
-      __syncthreads();  // Y slab (+ graph image) visible; the previous slab's readers of r_static / red are done
-      auto y_next = [&]() {  // issued once this slab has read Y for the last time
-        if (s + 1 < s1) {
-          y_fetch(b, s + 1);
-          y_ahead = true;
-        } else if (!list_mode && wk + gridDim.x < n_work) {
-          const int64_t wn = wk + gridDim.x;
-          const int64_t bn = wn / P.cpl;
-          y_fetch(bn, (int)(wn - bn * P.cpl) * P.CH);
-          y_ahead = true;
-        }
-      };
+      __syncthreads();  // Y slab (+ graph image) visible; the previous slab's readers of r_static / red / Y are done
+      const float4* y_static = y_buf + y_sel * Np;
+      // the NEXT slab's Y goes into the other buffer right away: a whole slab (~15 us) to arrive, instead of
+      // the one iteration the single-buffer version left it (its cp.async wait showed up as 6 % of the kernel)
+      if (s + 1 < s1) {
+        y_fetch(b, s + 1, y_sel ^ 1);
+        y_ahead = true;
+      } else if (!list_mode && wk + gridDim.x < n_work) {
+        const int64_t wn = wk + gridDim.x;
+        const int64_t bn = wn / P.cpl;
+        y_fetch(bn, (int)(wn - bn * P.cpl) * P.CH, y_sel ^ 1);
+        y_ahead = true;
+      }
 
       // ---- r0 = RHS - M Y ; p0 = im r0 ; p^s_0 = r0 ; x_u = x_s = Y
       V4 Xu[TPT], Xs[TPT], Pv[TPT], Ps[TPT], R[TPT], G[TPT];
@@ -360,7 +367,6 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
           }
           fs = true;
           Ts = k;
-          y_next();
         }
         if (stop_u) {
           if (So != nullptr) {
@@ -463,20 +469,20 @@ static BatchedFn ms_pick_t(int64_t N, int kq, int* threads) {
 BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn) {
   if (kq < 1 || kq > 4 || N < 1) return nullptr;
   BatchedFn f = nullptr;
-  // measured on B200 (B = 1440, N = 1200, k = 8): T x 2 rows 16.95 ms, T x 4 rows 16.68 ms, T x 5 rows with the
-  // graph in registers 16.14 ms (the two-solve kernel: 21.2 ms)
-  if (variant == 0) variant = kq <= 2 ? 3 : 2;
+  // measured on B200 (B = 1440, N = 1200, k = 8, packer included): T x 2 rows 16.46 ms, T x 4 rows 15.12 ms,
+  // T x 5 rows with the graph in registers 16.36 ms (the two-solve kernel: 21.2 ms)
+  if (variant == 0) variant = 2;
   if (variant == 3 && kq <= 2) {
     f = ms_pick_t<5, true, 256>(N, kq, threads);
     if (f != nullptr) {
-      *smem_dyn = 0;
+      *smem_dyn = (size_t)*threads * 5 * 32;  // the two Y-slab buffers
       return f;
     }
   }
   if (variant >= 2) {
     f = ms_pick_t<4, false, 320>(N, kq, threads);
     if (f != nullptr) {
-      *smem_dyn = (size_t)*threads * 4 * kq * (16 + 8);
+      *smem_dyn = (size_t)*threads * 4 * (kq * (16 + 8) + 32);  // graph image + the two Y-slab buffers
       return f;
     }
   }
@@ -489,7 +495,7 @@ BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* 
     }
   if (t == 0) return nullptr;
   *threads = t;
-  *smem_dyn = (size_t)t * 2 * kq * (16 + 8);
+  *smem_dyn = (size_t)t * 2 * (kq * (16 + 8) + 32);
   switch (t) {
     case 128: return ms_pick_kq<2, 128, false>(kq);
     case 256: return ms_pick_kq<2, 256, false>(kq);

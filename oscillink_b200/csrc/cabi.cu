@@ -50,7 +50,7 @@ int launch_knn_tc(const float* q_hi, const float* q_lo, const float* all_hi, con
                   int32_t* cand_idx, float* cand_sim, bool onepass, cudaStream_t st, bool f16 = false);
 int launch_rescore(const float*, const float*, int64_t, int64_t, int64_t, int64_t, int, const int32_t*,
                    const float*, int, int, float, int32_t*, float*, float*, int64_t*, int*, cudaStream_t,
-                   int64_t exhaustive_limit = -1);
+                   int64_t exhaustive_limit = -1, float* dedup_S = nullptr);
 int launch_assemble(const int32_t*, const float*, int64_t, int64_t, int, float, int32_t*, float*, float*,
                     int32_t*, float*, int64_t*, float*, cudaStream_t);
 int launch_receipt_full(const osc_graph_t*, const osc_params_t*, const float*, const float*,
@@ -240,7 +240,9 @@ int osc_knn_rescore(const float* Yn_q, const float* Yn_all, int64_t batch, int64
 
 int osc_knn_rescore_workspace(int64_t batch, int64_t n_rows, size_t* h_bytes) {
   OSC_REQUIRE(h_bytes != nullptr && batch >= 0 && n_rows >= 0, "knn_rescore_workspace: bad argument");
-  *h_bytes = align_up((size_t)batch * n_rows * sizeof(int64_t)) + 256;
+  // flagged-row list + the [rows][<= 32] score table of the duplicate-free re-scoring (knn_rescore_owned_kernel)
+  *h_bytes = align_up((size_t)batch * n_rows * sizeof(int64_t)) + 256 +
+             align_up((size_t)batch * n_rows * 32 * sizeof(float));
   return OSC_OK;
 }
 
@@ -259,8 +261,10 @@ int osc_knn_rescore_guarded(const float* Yn_q, const float* Yn_all, int64_t batc
   cudaStream_t st = (cudaStream_t)stream;
   OSC_CUDA(cudaMemsetAsync(top_idx, 0xFF, sizeof(int32_t) * batch * n_rows * k, st));
   OSC_CUDA(cudaMemsetAsync(top_sim, 0, sizeof(float) * batch * n_rows * k, st));
+  float* S = reinterpret_cast<float*>(static_cast<char*>(workspace) +
+                                      align_up((size_t)batch * n_rows * sizeof(int64_t)) + 256);
   return launch_rescore(Yn_q, Yn_all, batch, n_rows, row0, N, D, cand_idx, cand_sim, kc, k, eps, top_idx,
-                        top_sim, gap, static_cast<int64_t*>(workspace), d_n_flagged, st, exhaustive_limit);
+                        top_sim, gap, static_cast<int64_t*>(workspace), d_n_flagged, st, exhaustive_limit, S);
 }
 
 int osc_knn_rescore_checked(const float* Yn_q, const float* Yn_all, int64_t batch, int64_t n_rows,
@@ -387,6 +391,7 @@ int osc_knn_build_workspace(int64_t batch, int64_t N, int32_t D, int32_t k, int3
     b += align_up(rows * k * sizeof(int32_t)) + align_up(rows * k * sizeof(float));    // top-k
     b += align_up(rows * sizeof(float));                                               // cap scale
     b += align_up(rows * sizeof(int64_t)) + 512;                                       // flagged rows + counter
+    b += align_up(rows * 32 * sizeof(float));                                          // duplicate-free score table
     return b + 1024;
   };
   size_t b = layout(eng);
@@ -454,6 +459,7 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   float* cscale = ar.take<float>(rows);
   int64_t* flagged = ar.take<int64_t>(rows);
   int* n_flagged = ar.take<int>(1);
+  float* dedup_S = ar.take<float>(rows * 32);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "knn_build: workspace too small");
   if ((rc = launch_normalize(Y, (int64_t)rows, D, Yn, h16 ? nullptr : hi, lo, st, h16))) return rc;
   if ((rc = osc_knn_candidates(Yn, Yn, hi, lo, hi, lo, batch, N, 0, N, D, kc, eng, cand_idx, cand_sim,
@@ -464,7 +470,7 @@ int osc_knn_build(const float* Y, int64_t batch, int64_t N, int32_t D, int32_t k
   const bool guarded = may_fall_back && attempt == 0;
   const int64_t limit = guarded ? osc_knn_exhaustive_limit((int64_t)rows) : -1;
   if ((rc = launch_rescore(Yn, Yn, batch, N, 0, N, D, cand_idx, cand_sim, kc, k, engine_eps(eng), top_idx,
-                           top_sim, gap, flagged, n_flagged, st, limit)))
+                           top_sim, gap, flagged, n_flagged, st, limit, dedup_S)))
     return rc;
   if (guarded) {
     int h_flagged = 0;

@@ -346,6 +346,184 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
   }
 }
 
+// ---------------------------------------------------------------- re-scoring without duplicate dots
+// In a square problem (every row of a lattice is a query) a mutual candidate pair is scored twice by
+// knn_rescore_kernel: dot(i, j) by row i and dot(j, i) by row j -- the same fp64 sum, element for element
+// (the lane ownership of the elements is identical), and ~80 % of the kept candidates are mutual.  Here the
+// pair is computed ONCE, by the row with the smaller index:
+//   row i OWNS candidate j  iff  j > i  or  i is not among row j's kept candidates
+// (if j < i and i is kept by row j, then row j owns the pair because i > j).  Pass A computes the owned dots
+// and stores them in S[row][slot]; a slot it does not own receives a NaN whose payload is the slot of i in
+// row j's list.  Pass B resolves those slots from S[j][.] and ranks exactly as knn_rescore_kernel does.
+// The set of row fetches drops by ~40 %; results are bit-identical (tests: OSC_RESCORE_DEDUP=0 vs 1).
+__device__ __forceinline__ int kept_prefix(const float* __restrict__ cs, int kc, int k, float eps) {
+  if (kc <= k) return kc;
+  const float thr = cs[k] - 2.0f * eps;
+  int cnt = 0;
+  for (int c = 0; c < kc; ++c) cnt += (cs[c] >= thr) ? 1 : 0;
+  int n = cnt < k + 1 ? k + 1 : cnt;
+  return n > kc ? kc : n;
+}
+
+__global__ void __launch_bounds__(256, 4)
+knn_rescore_owned_kernel(const float* __restrict__ Yall, int64_t N, int D, const int32_t* __restrict__ cand_idx,
+                         const float* __restrict__ cand_sim, int kc, int k, float eps, float* __restrict__ S) {
+  extern __shared__ float smem[];
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* own_j = reinterpret_cast<int*>(smem) + (size_t)w * 2 * kc;  // [kc] owned columns, [kc] their slots
+  int* own_c = own_j + kc;
+  const int64_t b = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * warps + w;
+  if (r >= N) return;
+  const float* all = Yall + b * N * D;
+  const float* yi = all + r * D;
+  const int32_t* ci = cand_idx + (b * N + r) * kc;
+  const float* cs = cand_sim + (b * N + r) * kc;
+  float* Si = S + (b * N + r) * kc;
+  // the row's own kept prefix (same rule as knn_rescore_kernel)
+  int n_keep = kc;
+  if (kc > k) {
+    const float thr = cs[k] - 2.0f * eps;
+    const unsigned m = __ballot_sync(0xffffffffu, lane < kc && cs[lane < kc ? lane : 0] >= thr);
+    const int cnt = __popc(m);
+    n_keep = cnt < k + 1 ? k + 1 : cnt;
+    if (n_keep > kc) n_keep = kc;
+  }
+  // ownership of slot `lane`
+  int j = -1, pos = -1;
+  bool owned = false;
+  if (lane < n_keep) {
+    j = ci[lane];
+    if (j >= 0) {
+      owned = true;
+      if (j < r) {
+        const int32_t* cj = cand_idx + (b * N + j) * kc;
+        const float* csj = cand_sim + (b * N + j) * kc;
+        const int nk = kept_prefix(csj, kc, k, eps);
+        for (int c = 0; c < nk; ++c)
+          if (cj[c] == (int32_t)r) pos = c;
+        owned = pos < 0;
+      }
+    }
+  }
+  if (lane < kc && !owned) {  // (owned slots are written once, by the dot loop below)
+    float v = -INFINITY;      // slots beyond the kept prefix / invalid columns
+    if (lane < n_keep && j >= 0) v = __int_as_float(0x7fc00000 | pos);  // NaN, payload = slot in row j
+    Si[lane] = v;
+  }
+  const unsigned om = __ballot_sync(0xffffffffu, owned);
+  const int n_own = __popc(om);
+  if (owned) {
+    const int q = __popc(om & ((1u << lane) - 1u));
+    own_j[q] = j;
+    own_c[q] = lane;
+  }
+  __syncwarp();
+  const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(all)) % 16 == 0);
+  for (int c0 = 0; c0 < n_own; c0 += 4) {
+    int jc[4];
+    const float* yj[4];
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      jc[u] = (c0 + u < n_own) ? own_j[c0 + u] : -1;
+      yj[u] = jc[u] >= 0 ? all + (int64_t)jc[u] * D : yi;
+      acc[u] = 0.0;
+    }
+    if (v4) {  // same element ownership / order per lane as knn_rescore_kernel: bit-identical sums
+      for (int d = lane * 4; d < D; d += 128) {
+        const float4 q = *reinterpret_cast<const float4*>(yi + d);
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(yj[u] + d);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u] = fma((double)q.x, (double)x[u].x, acc[u]);
+          acc[u] = fma((double)q.y, (double)x[u].y, acc[u]);
+          acc[u] = fma((double)q.z, (double)x[u].z, acc[u]);
+          acc[u] = fma((double)q.w, (double)x[u].w, acc[u]);
+        }
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const double q = (double)yi[d];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(q, (double)yj[u][d], acc[u]);
+      }
+    }
+    const double tot = warp_sum4(acc, lane);
+    const int u = lane >> 3;
+    if ((lane & 7) == 0 && c0 + u < n_own) Si[own_c[c0 + u]] = (float)tot;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+knn_rescore_rank_kernel(int64_t N, const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_sim, int kc,
+                        int k, float eps, const float* __restrict__ S, int32_t* __restrict__ top_idx,
+                        float* __restrict__ top_sim, float* __restrict__ gap, int64_t* __restrict__ flagged,
+                        int* __restrict__ n_flagged) {
+  extern __shared__ float smem[];
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sv = smem + (size_t)w * kc;
+  int* sj = reinterpret_cast<int*>(smem + (size_t)warps * kc) + (size_t)w * kc;
+  const int64_t b = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * warps + w;
+  if (r >= N) return;
+  const int32_t* ci = cand_idx + (b * N + r) * kc;
+  const float* cs = cand_sim + (b * N + r) * kc;
+  const float* Si = S + (b * N + r) * kc;
+  int n_keep = kc;
+  if (kc > k) {
+    const float thr = cs[k] - 2.0f * eps;
+    const unsigned m = __ballot_sync(0xffffffffu, lane < kc && cs[lane < kc ? lane : 0] >= thr);
+    const int cnt = __popc(m);
+    n_keep = cnt < k + 1 ? k + 1 : cnt;
+    if (n_keep > kc) n_keep = kc;
+  }
+  if (lane < n_keep) {
+    const int j = ci[lane];
+    float v = Si[lane];
+    if (v != v) v = S[(b * N + j) * kc + (__float_as_int(v) & 0xff)];  // the pair was scored by row j
+    sv[lane] = j >= 0 ? v : -INFINITY;
+    sj[lane] = j;
+  }
+  __syncwarp();
+  const int64_t o = (b * N + r) * k;
+  float kth = INFINITY, nxt = -INFINITY;
+  for (int c = lane; c < n_keep; c += 32) {
+    const float s = sv[c];
+    const int j = sj[c];
+    if (j < 0) continue;
+    int rank = 0;
+    for (int c2 = 0; c2 < n_keep; ++c2) {
+      const int j2 = sj[c2];
+      if (j2 >= 0 && c2 != c && better(sv[c2], j2, s, j)) ++rank;
+    }
+    if (rank < k) {
+      top_idx[o + rank] = j;
+      top_sim[o + rank] = s;
+    }
+    if (rank == k - 1) kth = s;
+    if (rank == k) nxt = s;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
+    nxt = fmaxf(nxt, __shfl_xor_sync(0xffffffffu, nxt, off));
+  }
+  if (gap != nullptr && lane == 0) gap[b * N + r] = (nxt == -INFINITY) ? INFINITY : kth - nxt;
+  if (flagged != nullptr && (int64_t)kc < N - 1) {  // completeness check, as in knn_rescore_kernel
+    float amin = INFINITY;
+    for (int c = lane; c < kc; c += 32)
+      if (ci[c] >= 0) amin = fminf(amin, cs[c]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off));
+    if (lane == 0 && (kth == INFINITY || amin + eps >= kth)) flagged[atomicAdd(n_flagged, 1)] = b * N + r;
+  }
+}
+
 // ---------------------------------------------------------------- exhaustive fallback rows
 // One CTA per flagged row (grid-stride over the flagged list): every warp scans a strided subset of
 // the N columns with the same fp64-accumulated dot as the re-scoring pass and keeps its k+1 best in
@@ -496,7 +674,7 @@ int launch_knn_simt(const float* Yq, const float* Yall, int64_t batch, int64_t n
 int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t row0,
                    int64_t N, int D, const int32_t* cand_idx, const float* cand_sim, int kc, int k,
                    float eps, int32_t* top_idx, float* top_sim, float* gap, int64_t* flagged,
-                   int* n_flagged, cudaStream_t st, int64_t exhaustive_limit) {
+                   int* n_flagged, cudaStream_t st, int64_t exhaustive_limit, float* dedup_S) {
   const int warps = 8;
   const size_t smem = (size_t)warps * kc * (sizeof(float) + sizeof(int));
   dim3 grid((unsigned)((n_rows + warps - 1) / warps), (unsigned)batch);
@@ -506,6 +684,19 @@ int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_
   // resident warps per SM takes 10.6 ms, the variant that keeps the fp64 query row in registers
   // (128 registers, 16 warps) 16.0 ms -- latency hiding wins over the saved conversions.  Groups of 5
   // candidates (two groups instead of three for most rows, 80 registers, 24 warps) measured 12.8 ms.
+  bool dedup = dedup_S != nullptr && check && n_rows == N && row0 == 0 && Yq == Yall && kc <= 32 && kc > k;
+  {
+    const char* e = getenv("OSC_RESCORE_DEDUP");  // dev-only A/B switch
+    if (e && atoi(e) == 0) dedup = false;
+  }
+  if (dedup) {
+    const size_t sm_a = (size_t)warps * 2 * kc * sizeof(int);
+    knn_rescore_owned_kernel<<<grid, warps * 32, sm_a, st>>>(Yall, N, D, cand_idx, cand_sim, kc, k, eps, dedup_S);
+    OSC_LAUNCH_CHECK("knn_rescore_owned_kernel");
+    knn_rescore_rank_kernel<<<grid, warps * 32, smem, st>>>(N, cand_idx, cand_sim, kc, k, eps, dedup_S, top_idx,
+                                                            top_sim, gap, flagged, n_flagged);
+    OSC_LAUNCH_CHECK("knn_rescore_rank_kernel");
+  }
   auto fn = knn_rescore_kernel<0>;
   {
     const char* e = getenv("OSC_RESCORE_HOIST");  // dev-only A/B switch
@@ -514,9 +705,11 @@ int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_
            : D <= 256 ? knn_rescore_kernel<2>
            : D <= 384 ? knn_rescore_kernel<3> : knn_rescore_kernel<0>;
   }
-  fn<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k, top_idx, top_sim, gap,
-                                     check ? cand_sim : nullptr, eps, check ? flagged : nullptr, n_flagged);
-  OSC_LAUNCH_CHECK("knn_rescore_kernel");
+  if (!dedup) {
+    fn<<<grid, warps * 32, smem, st>>>(Yq, Yall, n_rows, N, D, cand_idx, kc, k, top_idx, top_sim, gap,
+                                       check ? cand_sim : nullptr, eps, check ? flagged : nullptr, n_flagged);
+    OSC_LAUNCH_CHECK("knn_rescore_kernel");
+  }
   if (check && (int64_t)kc < N - 1) {
     const size_t sm2 = (size_t)warps * (k + 1) * (sizeof(float) + sizeof(int)) + warps * sizeof(int);
     int64_t blocks = batch * n_rows;

@@ -12,6 +12,7 @@
 // block owns a contiguous row range, every thread keeps fp64 partial sums for its columns,
 // partials go to part[block][D] and a second tiny kernel reduces them in a fixed order
 // (run-to-run deterministic -- the stop test is a knife edge at large N).
+#include <cstdlib>
 #include <map>
 
 #include "pcg.cuh"
@@ -289,6 +290,157 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
   flush_partial<VEC>(acc, sh, part, dm.D, cg, col_ok);
 }
 
+// ---------------------------------------------------------------- SpMM, double-buffered staging
+// Same arithmetic as pcg_spmm_kernel for a gathered vector in ONE buffer (every case but the fused-P2P
+// view).  The graph chunk of the NEXT row block (neighbour ids, weights, degrees: contiguous in global
+// memory) is copied into the second shared-memory buffer with cp.async while the current chunk's rows are
+// being gathered: one barrier per chunk instead of two, and the staging latency (a dependent global load in
+// front of every chunk) disappears behind the gathers.  Row addresses are formed at the point of use
+// (one 64-bit multiply-add per fetch) instead of being staged as pointers: 8 instead of 12 bytes per entry.
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+}
+
+template <int VEC, bool RES0>
+__global__ void __launch_bounds__(256)
+pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
+                 const float* __restrict__ vec, int local_ids, float* __restrict__ out,
+                 float* __restrict__ Pout, double* __restrict__ part, int rch,
+                 const int* __restrict__ done) {
+  extern __shared__ double sh[];
+  if (done != nullptr && *done != 0) return;
+  const int CG = dm.D / VEC;
+  const int nthr = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  int32_t* s_id0 = reinterpret_cast<int32_t*>(sh + (size_t)nthr * VEC);
+  const size_t per_buf = (size_t)rch * (2 * g.k + 1);  // ids, weights, degrees (4-byte words)
+  const int64_t rpb = (dm.n_local + dm.n_blocks - 1) / dm.n_blocks;
+  const int64_t r_beg = (int64_t)blockIdx.x * rpb;
+  const int64_t r_end = min(dm.n_local, r_beg + rpb);
+  const float offc = op_offc(c), offp = op_offp(c);
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool col_ok = cg < CG;
+  const int co = cg * VEC;
+  auto stage = [&](int buf, int64_t c0, int rows) {
+    int32_t* ids = s_id0 + buf * per_buf;
+    float* ws = reinterpret_cast<float*>(ids + (size_t)rch * g.k);
+    int32_t* dg = reinterpret_cast<int32_t*>(ws + (size_t)rch * g.k);
+    const int n = rows * g.k;
+    for (int e = tid; e < n; e += nthr) {
+      cp_async4(ids + e, g.nbr + c0 * g.k + e);
+      cp_async4(ws + e, g.W + c0 * g.k + e);
+    }
+    for (int e = tid; e < rows; e += nthr) cp_async4(dg + e, g.deg + c0 + e);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  double acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+  if (r_beg < r_end) stage(0, r_beg, (int)min((int64_t)rch, r_end - r_beg));
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  int buf = 0;
+  for (int64_t c0 = r_beg; c0 < r_end; c0 += rch, buf ^= 1) {
+    const int rows = (int)min((int64_t)rch, r_end - c0);
+    if (c0 + rch < r_end) stage(buf ^ 1, c0 + rch, (int)min((int64_t)rch, r_end - (c0 + rch)));
+    const int32_t* ids = s_id0 + buf * per_buf;
+    const float* ws = reinterpret_cast<const float*>(ids + (size_t)rch * g.k);
+    const int32_t* dgs = reinterpret_cast<const int32_t*>(ws + (size_t)rch * g.k);
+    if (col_ok) {
+      for (int lr = threadIdx.y; lr < rows; lr += blockDim.y) {
+        const int64_t i = c0 + lr;
+        const int64_t gi = dm.row0 + i;
+        const float* own_p = vec + (local_ids ? i : gi) * dm.D + co;
+        float own[VEC], s[VEC];
+        ldv<VEC>(own_p, own);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+        const int n = dgs[lr];
+        const int32_t* nb = ids + lr * g.k;
+        const float* wt = ws + lr * g.k;
+        int t = 0;
+        for (; t + 8 <= n; t += 8) {
+          float x[8][VEC];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) ldv<VEC>(vec + (int64_t)nb[t + u] * dm.D + co, x[u]);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float w = wt[t + u];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+          }
+        }
+        if (t < n) {  // masked remainder batch (see pcg_spmm_kernel)
+          if (n - t > 4) {
+            float x[8][VEC];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ldv<VEC>(t + u < n ? vec + (int64_t)nb[t + u] * dm.D + co : own_p, x[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float w = t + u < n ? wt[t + u] : 0.f;
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+            }
+          } else {
+            float x[4][VEC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ldv<VEC>(t + u < n ? vec + (int64_t)nb[t + u] * dm.D + co : own_p, x[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float w = t + u < n ? wt[t + u] : 0.f;
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) s[v] = fmaf(w, x[u][v], s[v]);
+            }
+          }
+        }
+        const float b = gates ? gates[i] : 1.0f;
+        const float dg = op_diag(c, b);
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v] = dg * own[v] - offc * s[v];
+        if (ch.slot != nullptr && offp != 0.f) {
+          const int sl = ch.slot[gi];
+          if (sl >= 0) {
+            float sp[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sp[v] = 0.f;
+            for (int e = ch.rowptr[sl]; e < ch.rowptr[sl + 1]; ++e) {
+              float x[VEC];
+              ldv<VEC>(vec + (int64_t)ch.col[e] * dm.D + co, x);
+              const float w = ch.Wp[e];
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) sp[v] = fmaf(w, x[v], sp[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) o[v] -= offp * sp[v];
+          }
+        }
+        if constexpr (RES0) {
+          float bv[VEC], r[VEC], z[VEC];
+          ldv<VEC>(out + i * dm.D + co, bv);
+          const float md = md_diag(c, b);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            r[v] = bv[v] - o[v];
+            z[v] = precond(c, r[v], md);
+            acc[v] += (double)r[v] * (double)z[v];
+          }
+          stv<VEC>(out + i * dm.D + co, r);
+          stv<VEC>(Pout + i * dm.D + co, z);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += (double)own[v] * (double)o[v];
+          stv<VEC>(out + i * dm.D + co, o);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();  // the next chunk has landed; every reader of this buffer is done
+  }
+  flush_partial<VEC>(acc, sh, part, dm.D, cg, col_ok);
+}
+
 // ---------------------------------------------------------------- x, r update + partial rr, rz'
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -548,6 +700,34 @@ int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g, const 
   if (rch == 0) return fail(OSC_ERR_UNSUPPORTED, "pcg: ELL width too large for the staged SpMM");
   const size_t smem = spmm_smem_bytes(blk, vec, g->k, rch);
   const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
+  // one buffer holds the gathered vector (everything but the fused-P2P view): double-buffered staging
+  bool two = vv.peers == nullptr && vv.all != nullptr && rch >= 2;
+  {
+    static const int off = [] { const char* e = getenv("OSC_SPMM2"); return (e && atoi(e) == 0) ? 1 : 0; }();
+    if (off) two = false;  // dev-only A/B switch
+  }
+  if (two) {
+    // same bytes as the pointer staging: 2 buffers x rch x (8 k + 4) <= rch x (12 k + 4) + ... for k >= 1
+    const size_t smem2 = (size_t)blk.x * blk.y * vec * sizeof(double) + 2 * (size_t)rch * ((size_t)g->k * 8 + 4);
+#define OSC_SPMM2_LAUNCH(R0)                                                                              \
+  OSC_VEC_DISPATCH(vec, {                                                                                 \
+    if (smem2 > 48 * 1024)                                                                                \
+      OSC_CUDA(cudaFuncSetAttribute((const void*)pcg_spmm2_kernel<VEC, R0>,                               \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmmSmemMax));    \
+    pcg_spmm2_kernel<VEC, R0><<<grid, blk, smem2, st>>>(to_dims(d), c, gview(g), cview(chain), gates,     \
+                                                       vv.all, vv.local_ids, out, Pout, part, rch, done); \
+  })
+    if (smem2 <= kSpmmSmemMax) {
+      if (res0) {
+        OSC_SPMM2_LAUNCH(true)
+      } else {
+        OSC_SPMM2_LAUNCH(false)
+      }
+      OSC_LAUNCH_CHECK("pcg_spmm2_kernel");
+      return OSC_OK;
+    }
+#undef OSC_SPMM2_LAUNCH
+  }
 #define OSC_SPMM_LAUNCH(R0)                                                                               \
   OSC_VEC_DISPATCH(vec, {                                                                                 \
     if (smem > 48 * 1024)                                                                                 \

@@ -261,3 +261,25 @@ def test_multishift_uneven_slabs_forced_counts(monkeypatch):
     for i in (0, 1):
         assert np.linalg.norm(res["1"][i] - res["0"][i]) / np.linalg.norm(res["0"][i]) < 2e-6
     assert np.allclose(res["1"][4], res["0"][4], rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,D,k", [(1200, 384, 8), (500, 64, 6), (300, 36, 12)])
+def test_duplicate_free_rescoring_is_bit_identical(N, D, k, monkeypatch):
+    """knn_rescore_owned_kernel + knn_rescore_rank_kernel (every mutual candidate pair scored once) against
+    knn_rescore_kernel (every pair scored by both rows): identical neighbour tables, weights and gaps."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    Y, psi = _inputs(3, N, D, seed0=500)
+    Y[1, 7] = Y[1, 3]          # duplicate anchors: exact ties, handled by the canonical (sim desc, index asc) rule
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("OSC_RESCORE_DEDUP", flag)
+        bl = BatchedLattices(Y, kneighbors=k)
+        torch.cuda.synchronize()
+        res.append((bl.nbr.cpu().numpy(), bl.A.cpu().numpy(), bl.W.cpu().numpy(), bl.gap.cpu().numpy(),
+                    int(bl.n_exhaustive.item())))
+    for a, b in zip(res[0][:4], res[1][:4]):
+        assert np.array_equal(a, b)
+    assert res[0][4] == res[1][4]
