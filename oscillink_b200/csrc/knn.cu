@@ -356,18 +356,38 @@ knn_rescore_kernel(const float* __restrict__ Yq, const float* __restrict__ Yall,
 // and stores them in S[row][slot]; a slot it does not own receives a NaN whose payload is the slot of i in
 // row j's list.  Pass B resolves those slots from S[j][.] and ranks exactly as knn_rescore_kernel does.
 // The set of row fetches drops by ~40 %; results are bit-identical (tests: OSC_RESCORE_DEDUP=0 vs 1).
-__device__ __forceinline__ int kept_prefix(const float* __restrict__ cs, int kc, int k, float eps) {
-  if (kc <= k) return kc;
-  const float thr = cs[k] - 2.0f * eps;
-  int cnt = 0;
-  for (int c = 0; c < kc; ++c) cnt += (cs[c] >= thr) ? 1 : 0;
-  int n = cnt < k + 1 ? k + 1 : cnt;
-  return n > kc ? kc : n;
+// slot of `self` among the kept candidates of another row (-1: not kept).  The row's list is read with KC/4
+// independent 16-byte loads per array (a runtime loop serialises them: one L2 round trip per entry).
+template <int KC>
+__device__ __forceinline__ int kept_slot_of(const int32_t* __restrict__ cj, const float* __restrict__ csj, int k,
+                                            float eps, int32_t self) {
+  int32_t id[KC];
+  float sc[KC];
+#pragma unroll
+  for (int q = 0; q < KC / 4; ++q) {
+    const int4 a = reinterpret_cast<const int4*>(cj)[q];
+    const float4 f = reinterpret_cast<const float4*>(csj)[q];
+    id[4 * q] = a.x; id[4 * q + 1] = a.y; id[4 * q + 2] = a.z; id[4 * q + 3] = a.w;
+    sc[4 * q] = f.x; sc[4 * q + 1] = f.y; sc[4 * q + 2] = f.z; sc[4 * q + 3] = f.w;
+  }
+  const float thr = k < KC ? csj[k] - 2.0f * eps : -INFINITY;  // (a scalar load: indexing sc[] with the
+                                                                 //  run-time k would move it to local memory)
+  int cnt = 0, pos = -1;
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    cnt += (sc[c] >= thr) ? 1 : 0;
+    if (id[c] == self) pos = c;
+  }
+  int nk = cnt < k + 1 ? k + 1 : cnt;
+  if (nk > KC) nk = KC;
+  return pos < nk ? pos : -1;
 }
 
+template <int KC>
 __global__ void __launch_bounds__(256, 4)
 knn_rescore_owned_kernel(const float* __restrict__ Yall, int64_t N, int D, const int32_t* __restrict__ cand_idx,
-                         const float* __restrict__ cand_sim, int kc, int k, float eps, float* __restrict__ S) {
+                         const float* __restrict__ cand_sim, int k, float eps, float* __restrict__ S) {
+  constexpr int kc = KC;
   extern __shared__ float smem[];
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -398,11 +418,7 @@ knn_rescore_owned_kernel(const float* __restrict__ Yall, int64_t N, int D, const
     if (j >= 0) {
       owned = true;
       if (j < r) {
-        const int32_t* cj = cand_idx + (b * N + j) * kc;
-        const float* csj = cand_sim + (b * N + j) * kc;
-        const int nk = kept_prefix(csj, kc, k, eps);
-        for (int c = 0; c < nk; ++c)
-          if (cj[c] == (int32_t)r) pos = c;
+        pos = kept_slot_of<KC>(cand_idx + (b * N + j) * kc, cand_sim + (b * N + j) * kc, k, eps, (int32_t)r);
         owned = pos < 0;
       }
     }
@@ -684,14 +700,21 @@ int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_
   // resident warps per SM takes 10.6 ms, the variant that keeps the fp64 query row in registers
   // (128 registers, 16 warps) 16.0 ms -- latency hiding wins over the saved conversions.  Groups of 5
   // candidates (two groups instead of three for most rows, 80 registers, 24 warps) measured 12.8 ms.
-  bool dedup = dedup_S != nullptr && check && n_rows == N && row0 == 0 && Yq == Yall && kc <= 32 && kc > k;
+  bool dedup = dedup_S != nullptr && check && n_rows == N && row0 == 0 && Yq == Yall && kc > k &&
+               (kc == 16 || kc == 24 || kc == 32) && (reinterpret_cast<uintptr_t>(cand_idx) % 16 == 0) &&
+               (reinterpret_cast<uintptr_t>(cand_sim) % 16 == 0);
   {
     const char* e = getenv("OSC_RESCORE_DEDUP");  // dev-only A/B switch
     if (e && atoi(e) == 0) dedup = false;
   }
   if (dedup) {
     const size_t sm_a = (size_t)warps * 2 * kc * sizeof(int);
-    knn_rescore_owned_kernel<<<grid, warps * 32, sm_a, st>>>(Yall, N, D, cand_idx, cand_sim, kc, k, eps, dedup_S);
+    if (kc == 16)
+      knn_rescore_owned_kernel<16><<<grid, warps * 32, sm_a, st>>>(Yall, N, D, cand_idx, cand_sim, k, eps, dedup_S);
+    else if (kc == 24)
+      knn_rescore_owned_kernel<24><<<grid, warps * 32, sm_a, st>>>(Yall, N, D, cand_idx, cand_sim, k, eps, dedup_S);
+    else
+      knn_rescore_owned_kernel<32><<<grid, warps * 32, sm_a, st>>>(Yall, N, D, cand_idx, cand_sim, k, eps, dedup_S);
     OSC_LAUNCH_CHECK("knn_rescore_owned_kernel");
     knn_rescore_rank_kernel<<<grid, warps * 32, smem, st>>>(N, cand_idx, cand_sim, kc, k, eps, dedup_S, top_idx,
                                                             top_sim, gap, flagged, n_flagged);
