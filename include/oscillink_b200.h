@@ -335,6 +335,10 @@ typedef struct osc_dist {
   const int32_t* halo_rows;     /* [n_halo] ascending global ids of the remote rows this rank gathers */
   const int32_t* halo_nbr;      /* [n_local][k] neighbour ids as rows of P_block (-1 padded) */
   int64_t n_halo;
+  int64_t halo_below;           /* number of halo rows owned by lower ranks (ids < rank*shard): the pull starts
+                                   with the rows of rank+1 and wraps around, so that at any moment every
+                                   rank reads from a DIFFERENT peer (all ranks starting at peer 0 shared one
+                                   GPU's NVLink egress: 212 GB/s per GPU instead of 660 on 8 GPUs) */
 } osc_dist_t;
 
 /* NCCL version of the bound library (OSC_ERR_UNSUPPORTED if NCCL cannot be loaded) */

@@ -60,7 +60,8 @@ class Dist(C.Structure):
     """osc_dist_t: one rank's view of a sharded lattice (include/oscillink_b200.h)."""
     _fields_ = [("nccl_comm", c_void_p), ("world", c_i32), ("rank", c_i32), ("partition", c_i32),
                 ("halo", c_i32), ("N", c_i64), ("shard", c_i64), ("d_peer_P", c_void_p),
-                ("P_block", c_void_p), ("halo_rows", c_void_p), ("halo_nbr", c_void_p), ("n_halo", c_i64)]
+                ("P_block", c_void_p), ("halo_rows", c_void_p), ("halo_nbr", c_void_p), ("n_halo", c_i64),
+                ("halo_below", c_i64)]
 
 
 P = C.POINTER

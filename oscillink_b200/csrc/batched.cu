@@ -842,6 +842,7 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   // Fast path (batched_ms.cu): first settle (U = Y), uniform gates, settle + U* in one call -> the two
   // systems are shifts of one another and one multi-shift CG serves both.  Everything else (warm start,
   // gates, settle-only, N > 1280) takes the two-solve kernel below.
+  bool ms_two_ctas = false;
   bool use_ms = a->do_settle && a->do_ustar && a->U_in == nullptr && !gates && a->U_out != nullptr &&
                 a->dt > 0.f && prm->lamG + prm->lamQ > 0.f;
   {
@@ -850,12 +851,13 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   }
   if (use_ms) {
     int t_ms = 0, variant = 0;
+    ms_two_ctas = false;
     size_t smem_ms = 0;
     {
       const char* e = getenv("OSC_BATCHED_MS_VARIANT");  // dev-only: 1 = shared-memory-graph kernel
       if (e) variant = atoi(e);
     }
-    BatchedFn f = batched_ms_pick(N, kq, variant, &t_ms, &smem_ms);
+    BatchedFn f = batched_ms_pick(N, kq, variant, &t_ms, &smem_ms, &ms_two_ctas);
     if (f != nullptr) {
       fn = f;
       threads = t_ms;
@@ -878,6 +880,16 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
   if (use_ms) {
     OSC_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, threads, smem));
+    if (ms_two_ctas) {
+      // The tensor-memory variant is built for two CTAs per SM (256 TMEM columns each).  The occupancy
+      // calculator reports 1 for a kernel that allocates tensor memory (measured: grid 148, 10 warps per SM),
+      // although registers and shared memory admit two and two DO run side by side (13.9 vs 15.5 ms at
+      // B = 1440 with the grid doubled): size the grid from the kernel's own resource figures.
+      cudaFuncAttributes fa;
+      OSC_CUDA(cudaFuncGetAttributes(&fa, (const void*)fn));
+      const size_t per_cta = fa.sharedSizeBytes + smem + 1024;
+      if (2 * per_cta <= 228 * 1024 && 2 * (size_t)fa.numRegs * threads <= 65536) occ = 2;
+    }
   } else {
     if (threads == 640) {
       if (tpt <= 3) fn = pick_kq<3, 640, 1>(kq, gates);
@@ -900,10 +912,20 @@ int batched_settle(const osc_graph_t* g, const osc_params_t* prm, const osc_batc
     P.use_ybuf = (occ_y >= 1 && occ_y >= (occ < SCR_CTAS_PER_SM ? occ : SCR_CTAS_PER_SM)) ? 1 : 0;
     smem_launch = P.use_ybuf ? smem + batched_ybuf_smem(N) : smem;
   }
+  {
+    const char* e = getenv("OSC_BATCHED_OCC");  // dev-only: override the resident-CTA count per SM
+    if (e && atoi(e) >= 1) occ = atoi(e);
+  }
   if (occ < 1) return fail(OSC_ERR_UNSUPPORTED, "batched_settle: kernel does not fit on an SM");
   if (occ > SCR_CTAS_PER_SM) occ = SCR_CTAS_PER_SM;
   const int64_t resident = (int64_t)occ * sm_count();
   const unsigned grid = (unsigned)(P.n_work < resident ? P.n_work : resident);
+  {
+    const char* e = getenv("OSC_BATCHED_DEBUG");  // dev-only: launch geometry
+    if (e && atoi(e) != 0)
+      fprintf(stderr, "[osc] batched: ms=%d threads=%d smem_dyn=%zu occ=%d grid=%u n_work=%lld CH=%d\n", (int)use_ms,
+              threads, smem_launch, occ, grid, (long long)P.n_work, P.CH);
+  }
   fn<<<grid, threads, smem_launch, st>>>(P);
   OSC_LAUNCH_CHECK("batched_settle_kernel");
 

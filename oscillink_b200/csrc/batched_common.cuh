@@ -234,7 +234,7 @@ __device__ __forceinline__ V4 apply_row(const float4* p_s, const ushort4* nbr_s,
 
 // kernel entry type of the slab kernels and the selector of the multi-shift variant (batched_ms.cu)
 typedef void (*BatchedFn)(BatchedK);
-BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn);
+BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn, bool* two_ctas);
 float batched_sq_threshold(double tol);
 
 }  // namespace osc

@@ -55,6 +55,47 @@ __device__ __forceinline__ float block_total_cu(const float4* red, int lane) {
   return t;
 }
 
+// ---- tensor memory as thread-private state storage (TM variant) ---------------------------------------
+// TMEM (256 KB per SM: 128 lanes x 512 columns x 32 bit) is reachable from a SIMT kernel with tcgen05.ld/st.
+// In the 32x32b shape thread l of a warp addresses lane 32*(warp % 4) + l and .x4 moves four consecutive
+// columns = one float4 per thread: exactly the thread-private row state this kernel keeps.  Parking x_u, x_s
+// and p_s there (touched once per iteration) halves the register state, so TWO CTAs fit on an SM again and
+// one slab's latency-bound scalar / reduction phases overlap the other's gather pass.
+__device__ __forceinline__ void tm_st(uint32_t taddr, V4 v) {
+  const float2 a = upk2(v.lo), b = upk2(v.hi);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
+               "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(b.x)),
+               "r"(__float_as_uint(b.y))
+               : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+struct TmRegs {
+  uint32_t r0, r1, r2, r3;
+};
+__device__ __forceinline__ void tm_ld_issue(uint32_t taddr, TmRegs& t) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(t.r0), "=r"(t.r1), "=r"(t.r2), "=r"(t.r3)
+               : "r"(taddr));
+}
+// the wait names the destination registers, so no consumer can be scheduled in front of it
+__device__ __forceinline__ void tm_ld_wait(TmRegs& a) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a.r0), "+r"(a.r1), "+r"(a.r2), "+r"(a.r3)::"memory");
+}
+__device__ __forceinline__ void tm_ld_wait(TmRegs& a, TmRegs& b, TmRegs& c) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a.r0), "+r"(a.r1), "+r"(a.r2), "+r"(a.r3), "+r"(b.r0), "+r"(b.r1), "+r"(b.r2), "+r"(b.r3),
+                 "+r"(c.r0), "+r"(c.r1), "+r"(c.r2), "+r"(c.r3)::"memory");
+}
+__device__ __forceinline__ V4 tm_v4(const TmRegs& t) {
+  return V4{pk2(__uint_as_float(t.r0), __uint_as_float(t.r1)), pk2(__uint_as_float(t.r2), __uint_as_float(t.r3))};
+}
+__device__ __forceinline__ V4 tm_ld(uint32_t taddr) {
+  TmRegs t;
+  tm_ld_issue(taddr, t);
+  tm_ld_wait(t);
+  return tm_v4(t);
+}
+
 // sum_t W_t v[nbr_t] for one row whose graph entries (byte offsets, weights) sit in registers
 template <int KQ>
 __device__ __forceinline__ V4 gather_regs(const float4* src, const ushort4 (&j)[KQ], const float4 (&w)[KQ]) {
@@ -95,8 +136,8 @@ __device__ __forceinline__ V4 gather_smem(const float4* src, const ushort4* nbr_
   return gather_regs<KQ>(src, j, w);
 }
 
-template <int TPT, int KQ, int T, bool GREG>
-__global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
+template <int TPT, int KQ, int T, bool GREG, bool TM>
+__global__ void __launch_bounds__(T, TM ? 2 : 1) batched_ms_kernel(BatchedK P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int Np = T * TPT;
   constexpr int nw = T >> 5;
@@ -106,12 +147,14 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   __shared__ __align__(16) float4 redB[RED_F4];  // r.r partials
   __shared__ __align__(16) float sc[8 * 4];      // broadcast CG scalars published by warp 0 (see the loop)
   __shared__ int sflag[2];                       // stop verdicts {settle, stationary} of this iteration
+  __shared__ uint32_t tmem_slot;                 // TM: base address of this CTA's tensor-memory columns
+  constexpr int YB = TM ? 1 : 2;                 // Y-slab buffers (TM: two CTAs share the SM's shared memory)
   const int N = P.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // dynamic shared memory: two Y-slab buffers [2][Np] float4 (the 4 columns of Y of the current slab and,
   // prefetched with cp.async while it iterates, of the next one), then the graph image (GREG: none)
   float4* y_buf = reinterpret_cast<float4*>(smem_raw);
-  float4* w_s = y_buf + 2 * Np;                                        // [KQ][Np]
+  float4* w_s = y_buf + YB * Np;                                       // [KQ][Np]
   ushort4* nbr_s = reinterpret_cast<ushort4*>(w_s + (size_t)Np * KQ);  // [KQ][Np]
   if (!GREG) {
     for (int e = tid; e < Np * KQ; e += T) {
@@ -122,8 +165,27 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
   for (int e = tid; e < Np; e += T) {
     r_static[e] = f4_zero();
     y_buf[e] = f4_zero();
-    y_buf[Np + e] = f4_zero();
+    if (YB == 2) y_buf[Np + e] = f4_zero();
   }
+  // TM: 3 vectors x TPT rows x 4 columns per thread; warps w, w+4, w+8, ... share a lane quarter and take
+  // consecutive column ranges.  256 columns per CTA: two CTAs own the SM's 512.
+  constexpr uint32_t TM_COLS_PER_WARP = 3 * TPT * 4;
+  static_assert(!TM || ((T / 32 + 3) / 4) * TM_COLS_PER_WARP <= 256, "TM variant: state does not fit 256 TMEM columns");
+  uint32_t ta = 0;
+  if constexpr (TM) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(&tmem_slot)),
+                   "r"(256u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    ta = tmem_slot + ((32u * (uint32_t)(warp & 3)) << 16) + (uint32_t)(warp >> 2) * TM_COLS_PER_WARP;
+  }
+  // tensor-memory column of state vector v (0: x_u, 1: x_s, 2: p_s) of this thread's row m
+  auto tcol = [&](int v, int m) -> uint32_t { return ta + (uint32_t)((v * TPT + m) * 4); };
   if (tid < RED_F4) {
     redA[tid] = f4_zero();
     redB[tid] = f4_zero();
@@ -202,7 +264,7 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
     for (int s = s0; s < s1; ++s) {
       const int col = s * SC;
       const float4 psi4 = *reinterpret_cast<const float4*>(P.psi + b * P.D + col);
-      if (y_ahead) y_sel ^= 1;  // the slab prefetched during the previous one
+      if (y_ahead) y_sel ^= (YB - 1);  // the slab prefetched during the previous one
       else y_fetch(b, s, y_sel);
       cp_async_wait_all();
       y_ahead = false;
@@ -210,23 +272,28 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
       const float4* y_static = y_buf + y_sel * Np;
       // the NEXT slab's Y goes into the other buffer right away: a whole slab (~15 us) to arrive, instead of
       // the one iteration the single-buffer version left it (its cp.async wait showed up as 6 % of the kernel)
-      if (s + 1 < s1) {
-        y_fetch(b, s + 1, y_sel ^ 1);
-        y_ahead = true;
-      } else if (!list_mode && wk + gridDim.x < n_work) {
-        const int64_t wn = wk + gridDim.x;
-        const int64_t bn = wn / P.cpl;
-        y_fetch(bn, (int)(wn - bn * P.cpl) * P.CH, y_sel ^ 1);
-        y_ahead = true;
-      }
+      auto y_next = [&]() {
+        if (s + 1 < s1) {
+          y_fetch(b, s + 1, y_sel ^ (YB - 1));
+          y_ahead = true;
+        } else if (!list_mode && wk + gridDim.x < n_work) {
+          const int64_t wn = wk + gridDim.x;
+          const int64_t bn = wn / P.cpl;
+          y_fetch(bn, (int)(wn - bn * P.cpl) * P.CH, y_sel ^ (YB - 1));
+          y_ahead = true;
+        }
+      };
+      if (YB == 2) y_next();  // (one buffer: issued once this slab has read Y for the last time, at stop_s)
 
       // ---- r0 = RHS - M Y ; p0 = im r0 ; p^s_0 = r0 ; x_u = x_s = Y
-      V4 Xu[TPT], Xs[TPT], Pv[TPT], Ps[TPT], R[TPT], G[TPT];
+      constexpr int XR = TM ? 1 : TPT;  // x_u, x_s, p_s: registers, or tensor memory (TM)
+      V4 Xu[XR], Xs[XR], Ps[XR], Pv[TPT], R[TPT], G[TPT];
       V4 part = v4_zero();
 #pragma unroll
       for (int m = 0; m < TPT; ++m) {
         const int row = tid + T * m;
-        Xu[m] = Xs[m] = Pv[m] = Ps[m] = R[m] = G[m] = v4_zero();
+        Pv[m] = R[m] = G[m] = v4_zero();
+        if (!TM) Xu[TM ? 0 : m] = Xs[TM ? 0 : m] = Ps[TM ? 0 : m] = v4_zero();
         if (wact[m]) {
           const float4 y = y_static[row];
           const V4 g0 = GREG ? gather_regs<KQ>(y_static, jj[GREG ? m : 0], ww[GREG ? m : 0])
@@ -239,15 +306,22 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
                                                __fadd_rn(__fmul_rn(P.lamG, y.w), __fmul_rn(P.lamQ, psi4.w)))
                                  : f4_zero();
           const V4 yv = to_v4(y);
-          Xu[m] = yv;
-          Xs[m] = yv;
           R[m] = v4_sub(to_v4(rhs), combine_row(yv, g0, diag, noffc));
           Pv[m] = v4_mul(IM, R[m]);
-          Ps[m] = R[m];
+          if constexpr (TM) {
+            tm_st(tcol(0, m), yv);
+            tm_st(tcol(1, m), yv);
+            tm_st(tcol(2, m), R[m]);
+          } else {
+            Xu[TM ? 0 : m] = yv;
+            Xs[TM ? 0 : m] = yv;
+            Ps[TM ? 0 : m] = R[m];
+          }
           part = v4_fma(R[m], R[m], part);
           sts_v4(r_static + row, R[m]);
         }
       }
+      if constexpr (TM) tm_wait_st();
       warp_reduce4(to_f4(part), redB + warp, lane);
       __syncthreads();  // r0 visible, r0.r0 partials visible
       // The CG scalars are the same for every warp.  WARP 0 ALONE evaluates them (per column: lane & 3) and
@@ -308,13 +382,24 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
           for (int m = 0; m < TPT; ++m) {
             if (wact[m]) {
               const V4 ap = combine_row(Pv[m], G[m], diag, noffc);
-              Xu[m] = v4_fma(Pv[m], AU, Xu[m]);
-              Xs[m] = v4_fma(Ps[m], AS, Xs[m]);
+              if constexpr (TM) {
+                TmRegs t0, t1, t2;
+                tm_ld_issue(tcol(0, m), t0);
+                tm_ld_issue(tcol(1, m), t1);
+                tm_ld_issue(tcol(2, m), t2);
+                tm_ld_wait(t0, t1, t2);
+                tm_st(tcol(0, m), v4_fma(Pv[m], AU, tm_v4(t0)));
+                tm_st(tcol(1, m), v4_fma(tm_v4(t2), AS, tm_v4(t1)));
+              } else {
+                Xu[TM ? 0 : m] = v4_fma(Pv[m], AU, Xu[TM ? 0 : m]);
+                Xs[TM ? 0 : m] = v4_fma(Ps[TM ? 0 : m], AS, Xs[TM ? 0 : m]);
+              }
               R[m] = v4_fma(ap, NAL, R[m]);
               part = v4_fma(R[m], R[m], part);
               sts_v4(r_static + tid + T * m, R[m]);
             }
           }
+          if constexpr (TM) tm_wait_st();
         }
         warp_reduce4(to_f4(part), redB + warp, lane);
         __syncthreads();  // B2: r_{k+1} visible, r.r partials visible
@@ -360,19 +445,30 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
           const V4 SG = v4_bc(sigma);
 #pragma unroll
           for (int m = 0; m < TPT; ++m) {
-            const int row = tid + T * m;
-            if (act[m]) *reinterpret_cast<float4*>(Uo + (int64_t)row * P.D + col) = to_f4(Xs[m]);
-            const V4 dy = v4_sub(lds_v4(y_static + row), Xs[m]);
-            Ps[m] = v4_sub(v4_mul(SG, dy), v4_mul(ZN, R[m]));
+            if (wact[m]) {
+              const int row = tid + T * m;
+              const V4 xs = TM ? tm_ld(tcol(1, m)) : Xs[TM ? 0 : m];
+              if (act[m]) *reinterpret_cast<float4*>(Uo + (int64_t)row * P.D + col) = to_f4(xs);
+              const V4 dy = v4_sub(lds_v4(y_static + row), xs);
+              const V4 t1 = v4_sub(v4_mul(SG, dy), v4_mul(ZN, R[m]));
+              if constexpr (TM) tm_st(tcol(2, m), t1);
+              else Ps[TM ? 0 : m] = t1;
+            }
           }
+          if constexpr (TM) tm_wait_st();
           fs = true;
           Ts = k;
+          if (YB == 1) y_next();
         }
         if (stop_u) {
           if (So != nullptr) {
 #pragma unroll
-            for (int m = 0; m < TPT; ++m)
-              if (act[m]) *reinterpret_cast<float4*>(So + (int64_t)(tid + T * m) * P.D + col) = to_f4(Xu[m]);
+            for (int m = 0; m < TPT; ++m) {
+              if (wact[m]) {
+                const V4 xu = TM ? tm_ld(tcol(0, m)) : Xu[TM ? 0 : m];
+                if (act[m]) *reinterpret_cast<float4*>(So + (int64_t)(tid + T * m) * P.D + col) = to_f4(xu);
+              }
+            }
           }
           if (!fs) {  // the settle system needs more iterations: park r_{T_u} (thread-private rows)
 #pragma unroll
@@ -390,8 +486,15 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
           Pv[m] = v4_fma(Pv[m], BETA, v4_mul(IM, R[m]));
-          if (!fs) Ps[m] = v4_fma(Ps[m], BS, v4_mul(ZN, R[m]));
+          if (!fs && wact[m]) {
+            // (folding this into the next update phase -- one tensor-memory visit per row and iteration --
+            //  was tried: the two extra broadcast operands pushed the 96-register build into spills,
+            //  13.9 -> 17.9 ms at B = 1440)
+            if constexpr (TM) tm_st(tcol(2, m), v4_fma(tm_ld(tcol(2, m)), BS, v4_mul(ZN, R[m])));
+            else Ps[TM ? 0 : m] = v4_fma(Ps[TM ? 0 : m], BS, v4_mul(ZN, R[m]));
+          }
         }
+        if constexpr (TM) tm_wait_st();
       }
       if (tid == 0) {
         P.rec[(b * 2 + 0) * P.G + s] = make_int2(Ts, __float_as_int(rrs_rec));
@@ -402,9 +505,21 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
         float4 dpart = f4_zero();
 #pragma unroll
         for (int m = 0; m < TPT; ++m) {
+          if (!wact[m]) continue;
           float4 ru = to_f4(R[m]);
           if (ru_in_scr) ru = act[m] ? scr[tid + T * m] : f4_zero();
-          const float4 xs = to_f4(Xs[m]), xu = to_f4(Xu[m]), t1 = to_f4(Ps[m]);
+          V4 vxs, vxu, vt1;
+          if constexpr (TM) {
+            TmRegs t0, t1r, t2;
+            tm_ld_issue(tcol(0, m), t0);
+            tm_ld_issue(tcol(1, m), t1r);
+            tm_ld_issue(tcol(2, m), t2);
+            tm_ld_wait(t0, t1r, t2);
+            vxu = tm_v4(t0); vxs = tm_v4(t1r); vt1 = tm_v4(t2);
+          } else {
+            vxu = Xu[TM ? 0 : m]; vxs = Xs[TM ? 0 : m]; vt1 = Ps[TM ? 0 : m];
+          }
+          const float4 xs = to_f4(vxs), xu = to_f4(vxu), t1 = to_f4(vt1);
           const float4 d = make_float4(__fsub_rn(xs.x, xu.x), __fsub_rn(xs.y, xu.y), __fsub_rn(xs.z, xu.z),
                                        __fsub_rn(xs.w, xu.w));
           dpart = f4_add(dpart, f4_mul(d, f4_add(t1, ru)));
@@ -416,6 +531,14 @@ __global__ void __launch_bounds__(T, 1) batched_ms_kernel(BatchedK P) {
           if (lane == 0) P.dh_part[b * P.G + s] = (double)((tot.x + tot.y) + (tot.z + tot.w));
         }
       }
+    }
+  }
+  if constexpr (TM) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(256u));
     }
   }
 }
@@ -432,29 +555,29 @@ float batched_sq_threshold(double tol) {
   return x;
 }
 
-template <int TPT, int T, bool GREG>
+template <int TPT, int T, bool GREG, bool TM = false>
 static BatchedFn ms_pick_kq(int kq) {
-  if constexpr (GREG) {
-    return kq == 1 ? batched_ms_kernel<TPT, 1, T, true> : batched_ms_kernel<TPT, 2, T, true>;
+  if constexpr (GREG || TM) {
+    return kq == 1 ? batched_ms_kernel<TPT, 1, T, GREG, TM> : batched_ms_kernel<TPT, 2, T, GREG, TM>;
   } else {
     switch (kq) {
-      case 1: return batched_ms_kernel<TPT, 1, T, false>;
-      case 2: return batched_ms_kernel<TPT, 2, T, false>;
-      case 3: return batched_ms_kernel<TPT, 3, T, false>;
-      default: return batched_ms_kernel<TPT, 4, T, false>;
+      case 1: return batched_ms_kernel<TPT, 1, T, false, false>;
+      case 2: return batched_ms_kernel<TPT, 2, T, false, false>;
+      case 3: return batched_ms_kernel<TPT, 3, T, false, false>;
+      default: return batched_ms_kernel<TPT, 4, T, false, false>;
     }
   }
 }
 
 // smallest block (multiple of 32 threads, at most TMAX) whose T x TPT rows cover N
-template <int TPT, bool GREG, int TMAX>
+template <int TPT, bool GREG, int TMAX, bool TM = false>
 static BatchedFn ms_pick_t(int64_t N, int kq, int* threads) {
   const int64_t t = ((N + TPT - 1) / TPT + 31) / 32 * 32;
   if (t > TMAX) return nullptr;
   *threads = (int)t;
 #define OSC_MS_CASE(TT) \
   case TT:              \
-    if constexpr (TT <= TMAX) return ms_pick_kq<TPT, TT, GREG>(kq); else return nullptr;
+    if constexpr (TT <= TMAX) return ms_pick_kq<TPT, TT, GREG, TM>(kq); else return nullptr;
   switch ((int)t) {
     OSC_MS_CASE(32) OSC_MS_CASE(64) OSC_MS_CASE(96) OSC_MS_CASE(128) OSC_MS_CASE(160) OSC_MS_CASE(192)
     OSC_MS_CASE(224) OSC_MS_CASE(256) OSC_MS_CASE(288) OSC_MS_CASE(320)
@@ -465,13 +588,23 @@ static BatchedFn ms_pick_t(int64_t N, int kq, int* threads) {
 
 // The multi-shift kernel that serves (N, kq), its block size and dynamic shared memory; nullptr if none.
 // variant (dev A/B): 0 = auto, 1 = T x 2 rows + shared-memory graph, 2 = T x 4 rows + shared-memory graph,
-// 3 = T x 5 rows + graph in registers
-BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn) {
+// 3 = T x 5 rows + graph in registers, 4 = T x 4 rows, x_u / x_s / p_s in tensor memory, two CTAs per SM
+BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn, bool* two_ctas) {
+  *two_ctas = false;
   if (kq < 1 || kq > 4 || N < 1) return nullptr;
   BatchedFn f = nullptr;
   // measured on B200 (B = 1440, N = 1200, k = 8, packer included): T x 2 rows 16.46 ms, T x 4 rows 15.12 ms,
-  // T x 5 rows with the graph in registers 16.36 ms (the two-solve kernel: 21.2 ms)
-  if (variant == 0) variant = 2;
+  // T x 5 rows with the graph in registers 16.36 ms, T x 4 rows with x_u / x_s / p_s in tensor memory and two
+  // CTAs per SM 13.87 ms (the two-solve kernel: 21.2 ms)
+  if (variant == 0) variant = kq <= 2 ? 4 : 2;
+  if (variant == 4 && kq <= 2) {  // x_u, x_s, p_s in tensor memory: two CTAs per SM
+    f = ms_pick_t<4, false, 320, true>(N, kq, threads);
+    if (f != nullptr) {
+      *smem_dyn = (size_t)*threads * 4 * (kq * (16 + 8) + 16);  // graph image + ONE Y-slab buffer
+      *two_ctas = true;
+      return f;
+    }
+  }
   if (variant == 3 && kq <= 2) {
     f = ms_pick_t<5, true, 256>(N, kq, threads);
     if (f != nullptr) {

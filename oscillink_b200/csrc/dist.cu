@@ -210,12 +210,16 @@ int dist_halo_plan(const int32_t* nbr_loc, int64_t n_local, int k, const int32_t
 template <int VEC>
 __global__ void __launch_bounds__(256)
 halo_pull_kernel(const float* const* __restrict__ peers, const int32_t* __restrict__ halo_rows, int64_t n_halo,
-                 int64_t shard, int D, float* __restrict__ block, const int* __restrict__ done) {
+                 int64_t rot, int64_t shard, int D, float* __restrict__ block, const int* __restrict__ done) {
   if (done != nullptr && *done != 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t h = w0; h < n_halo; h += nwarps) {
+  for (int64_t v = w0; v < n_halo; v += nwarps) {
+    // the list is ordered by owner; rank r walks it from its first row above the own block and wraps:
+    // owners r+1, ..., G-1, 0, ..., r-1 -- a different source for every rank at every moment
+    int64_t h = v + rot;
+    if (h >= n_halo) h -= n_halo;
     const int64_t j = halo_rows[h];
     const int64_t g = j / shard;
     const float* src = peers[g] + (j - g * shard) * D;
@@ -237,11 +241,13 @@ static int halo_pull(const osc_dist_t* ds, int D, const int* done, cudaStream_t 
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(ds->P_block) & 15) == 0);
+  int64_t rot = ds->halo_below;
+  if (rot < 0 || rot >= ds->n_halo) rot = 0;
   if (v4)
-    halo_pull_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(ds->d_peer_P, ds->halo_rows, ds->n_halo, ds->shard, D,
+    halo_pull_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(ds->d_peer_P, ds->halo_rows, ds->n_halo, rot, ds->shard, D,
                                                           ds->P_block, done);
   else
-    halo_pull_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(ds->d_peer_P, ds->halo_rows, ds->n_halo, ds->shard, D,
+    halo_pull_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(ds->d_peer_P, ds->halo_rows, ds->n_halo, rot, ds->shard, D,
                                                           ds->P_block, done);
   OSC_LAUNCH_CHECK("halo_pull_kernel");
   return OSC_OK;

@@ -375,6 +375,8 @@ class _PullHalo:
             tab[rank] = p.value
         self.tab = torch.tensor(tab, dtype=torch.int64, device=dev)
         self.halo_fraction = self.n_halo / max(lat.N - nl, 1)  # share of the remote rows that is needed
+        # halo rows owned by lower ranks: the pull starts behind them (osc_dist_t.halo_below)
+        self.n_below = int((self.halo_rows[: self.n_halo] < r0).sum().item()) if self.n_halo else 0
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
 
@@ -776,12 +778,12 @@ class ShardedLattice:
         ds = cabi.Dist(self._nccl_comm() or None, self.world, self.rank,
                        cabi.PART_ROWS if rows else cabi.PART_COLUMNS,
                        cabi.HALO_PULL if pull else cabi.HALO_ALLGATHER, self.N, self.shard,
-                       None, None, None, None, 0)
+                       None, None, None, None, 0, 0)
         if pull:
             pl = self._pull
             ds.d_peer_P, ds.P_block = pl.tab.data_ptr(), pl.block_ptr
             ds.halo_rows = pl.halo_rows.data_ptr() if pl.n_halo else None
-            ds.halo_nbr, ds.n_halo = pl.nbr_local.data_ptr(), pl.n_halo
+            ds.halo_nbr, ds.n_halo, ds.halo_below = pl.nbr_local.data_ptr(), pl.n_halo, pl.n_below
         return ds
 
     def _use_c_path(self) -> bool:

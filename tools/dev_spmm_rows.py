@@ -7,6 +7,15 @@ sys.path.insert(0, ".")
 from oscillink_b200.sharded_api import ShardedLattice, _NativeKernels
 from oscillink_b200 import _cabi
 
+if os.environ.get("L2G"):  # experiment: cudaLimitMaxL2FetchGranularity (0x05) = 32 / 64 / 128 bytes
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    torch.cuda.init(); torch.zeros(1, device="cuda")
+    val = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5); before = val.value
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2G"])))
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print("L2 fetch granularity: before", before, "set rc", rc, "now", val.value)
 N = int(os.environ.get("N", "10000000")); D = int(os.environ.get("D", "48")); K = int(os.environ.get("K", "10"))
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 Y = torch.randn((N, D), generator=g, device="cuda")
