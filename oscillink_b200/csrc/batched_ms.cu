@@ -81,6 +81,10 @@ __device__ __forceinline__ void tm_ld_issue(uint32_t taddr, TmRegs& t) {
 __device__ __forceinline__ void tm_ld_wait(TmRegs& a) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a.r0), "+r"(a.r1), "+r"(a.r2), "+r"(a.r3)::"memory");
 }
+__device__ __forceinline__ void tm_ld_wait(TmRegs& a, TmRegs& b) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a.r0), "+r"(a.r1), "+r"(a.r2), "+r"(a.r3), "+r"(b.r0), "+r"(b.r1), "+r"(b.r2), "+r"(b.r3)::"memory");
+}
 __device__ __forceinline__ void tm_ld_wait(TmRegs& a, TmRegs& b, TmRegs& c) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(a.r0), "+r"(a.r1), "+r"(a.r2), "+r"(a.r3), "+r"(b.r0), "+r"(b.r1), "+r"(b.r2), "+r"(b.r3),
@@ -368,33 +372,35 @@ __global__ void __launch_bounds__(T, TM ? 2 : 1) batched_ms_kernel(BatchedK P) {
           ratio = zeta != 0.f ? __fdividef(zn, zeta) : 0.f;
           if (lane < 4) {
             sc[0 * 4 + lane] = alpha;
-            sc[1 * 4 + lane] = -alpha;
-            sc[2 * 4 + lane] = fs ? 0.f : a * ratio;
-            sc[3 * 4 + lane] = fu ? 0.f : alpha;
+            sc[2 * 4 + lane] = a * ratio;
           }
         }
         __syncthreads();  // B1b: step lengths published
         {
-          const V4 NAL = lds_v4(sc + 4), AS = lds_v4(sc + 8), AU = lds_v4(sc + 12);
+          // (alpha, a^s) only: r -= alpha A p is formed as fma(-(A p), alpha, r) with the negated operator row
+          //  -- bit-identical, and no -alpha operand to keep live; a frozen system's update is skipped by a
+          //  uniform branch instead of a zero step length)
+          const V4 AL = lds_v4(sc + 0), AS = lds_v4(sc + 8);
           // ---- x_u += alpha p ; x_s += a^s p^s ; r -= alpha A p ; publish r ; r.r
           part = v4_zero();
 #pragma unroll
           for (int m = 0; m < TPT; ++m) {
             if (wact[m]) {
-              const V4 ap = combine_row(Pv[m], G[m], diag, noffc);
               if constexpr (TM) {
-                TmRegs t0, t1, t2;
-                tm_ld_issue(tcol(0, m), t0);
-                tm_ld_issue(tcol(1, m), t1);
-                tm_ld_issue(tcol(2, m), t2);
-                tm_ld_wait(t0, t1, t2);
-                tm_st(tcol(0, m), v4_fma(Pv[m], AU, tm_v4(t0)));
-                tm_st(tcol(1, m), v4_fma(tm_v4(t2), AS, tm_v4(t1)));
+                if (!fu) tm_st(tcol(0, m), v4_fma(Pv[m], AL, tm_ld(tcol(0, m))));
+                if (!fs) {
+                  TmRegs t1, t2;
+                  tm_ld_issue(tcol(1, m), t1);
+                  tm_ld_issue(tcol(2, m), t2);
+                  tm_ld_wait(t1, t2);
+                  tm_st(tcol(1, m), v4_fma(tm_v4(t2), AS, tm_v4(t1)));
+                }
               } else {
-                Xu[TM ? 0 : m] = v4_fma(Pv[m], AU, Xu[TM ? 0 : m]);
-                Xs[TM ? 0 : m] = v4_fma(Ps[TM ? 0 : m], AS, Xs[TM ? 0 : m]);
+                if (!fu) Xu[TM ? 0 : m] = v4_fma(Pv[m], AL, Xu[TM ? 0 : m]);
+                if (!fs) Xs[TM ? 0 : m] = v4_fma(Ps[TM ? 0 : m], AS, Xs[TM ? 0 : m]);
               }
-              R[m] = v4_fma(ap, NAL, R[m]);
+              const V4 nap = combine_row(Pv[m], G[m], -diag, -noffc);  // -(A p)
+              R[m] = v4_fma(nap, AL, R[m]);
               part = v4_fma(R[m], R[m], part);
               sts_v4(r_static + tid + T * m, R[m]);
             }
