@@ -283,3 +283,21 @@ def test_duplicate_free_rescoring_is_bit_identical(N, D, k, monkeypatch):
     for a, b in zip(res[0][:4], res[1][:4]):
         assert np.array_equal(a, b)
     assert res[0][4] == res[1][4]
+
+
+def test_settle_host_batch_returns_the_settled_state():
+    """settle_host_batch(U_host=...): the settled U of every lattice comes back through a third stream."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices, settle_host_batch
+
+    B, N, D, k = 5, 200, 32, 6
+    Y, psi = _inputs(B, N, D, seed0=700)
+    Yh, ph = torch.from_numpy(Y).pin_memory(), torch.from_numpy(psi).pin_memory()
+    Uh = torch.empty((B, N, D), dtype=torch.float32).pin_memory()
+    got = settle_host_batch(Yh, ph, kneighbors=k, chunk=2, U_host=Uh).numpy()
+    bl = BatchedLattices(Y, kneighbors=k)
+    bl.set_query(psi)
+    out = bl.settle(receipt=True)
+    assert np.array_equal(got[:, 0], out["iters"].cpu().numpy().astype(np.float64))
+    assert np.array_equal(Uh.numpy(), bl.U.cpu().numpy())

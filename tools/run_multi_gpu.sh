@@ -1,20 +1,12 @@
 #!/bin/bash
 # Multi-GPU measurement recipe (run on the GPU box under gpurun --gpus G):
-#   tools/run_multi_gpu.sh G TAG [N D K CHAIN] [SERVING=1]
-G=${1:-2}; TAG=${2:-mg}; N=${3:-1000000}; D=${4:-768}; K=${5:-16}; CH=${6:-0}; SERVING=${7:-1}
+#   tools/run_multi_gpu.sh G TAG
+# 1. the NCCL parity test (rows + pull halo, rows + all-gather, column slabs vs the single-GPU class)
+# 2. the driver's own bench command: serving replicas + the sharded N=10M and N=1M lattices in one JSON line
+G=${1:-2}; TAG=${2:-mg}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1"
 mkdir -p gpurun_out
-for MODE in rows columns; do
-  timeout 300 $TR --master-port 29511 tools/sharded_check.py --N 20000 --D 384 --k 10 --mode $MODE \
-    > gpurun_out/${TAG}_check_${MODE}.json 2> gpurun_out/${TAG}_check_${MODE}.err
-  tail -1 gpurun_out/${TAG}_check_${MODE}.json | cut -c1-600
-done
-# rows with the fused P2P halo + columns (one build), then rows with the NCCL all-gather halo
-timeout 1500 $TR --master-port 29512 bench.py --gpus $G --workload large --N $N --D $D --k $K --chain-len $CH \
-  --partition both --steps 3 --warmup 1 > gpurun_out/${TAG}_large.json 2> gpurun_out/${TAG}_large.err
-tail -1 gpurun_out/${TAG}_large.json | cut -c1-3500; tail -3 gpurun_out/${TAG}_large.err
-if [ "$SERVING" = "1" ]; then
-  timeout 600 $TR --master-port 29513 bench.py --gpus $G --steps 3 --warmup 3 --no-large \
-    > gpurun_out/${TAG}_serving.json 2> gpurun_out/${TAG}_serving.err
-  tail -1 gpurun_out/${TAG}_serving.json | cut -c1-1500; tail -3 gpurun_out/${TAG}_serving.err
-fi
+python -m pytest tests/test_gpu_sharded.py -x -q -k nccl 2>&1 | tail -3
+timeout 1500 $TR --master-port 29512 bench.py --gpus $G --steps 5 --warmup 3 \
+  > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+tail -c 1500 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
