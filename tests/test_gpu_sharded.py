@@ -1,6 +1,7 @@
-"""GPU test of the sharded lattice: two ranks (gloo, both on cuda:0 -- the test box has one GPU;
-NCCL runs of the same code are in tools/sharded_check.py) against the single-GPU class and the
-reference golden values."""
+"""GPU tests of the sharded lattice against the single-GPU class and the reference golden values:
+two gloo ranks on cuda:0 (the Python-driven phase schedule, incl. the IPC-mapped fused halo), the C-ABI
+distributed solve at world 1, the halo plan, and -- whenever two or more GPUs are visible -- real NCCL
+ranks through osc_dist_pcg_solve (test_nccl_ranks_match_single_gpu; the round-1 tools/sharded_check.py)."""
 import os
 import socket
 
