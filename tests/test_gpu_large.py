@@ -145,3 +145,36 @@ def test_large_lattice_sampled_rows_and_properties(api):
     rec = lat.receipt()
     assert rec["deltaH_total"] >= 0.0
     assert rec["meta"]["ustar_converged"]
+
+
+def test_n1m_sampled_rows_against_exhaustive_fp64_scan(api):
+    """SURVEY 8(c) at the size of BASELINE configs[3]: N = 1M anchors; 32 random rows' mutual-kNN sets from an
+    exhaustive fp64 scan of the sample and of its neighbours (tools/sampled_check.py, the checker bench.py's
+    `parity_sample` uses) against the lattice's graph, plus the fp64 operator residual of U on a strided sample."""
+    import torch
+
+    from oscillink_b200.sharded_api import ShardedLattice
+    from tools import sampled_check as sc
+
+    N, D, k = 1_000_000, 64, 10
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    Y = torch.randn((N, D), generator=g, device="cuda")
+    lat = ShardedLattice(Y, N, kneighbors=k)
+    gs = torch.Generator()
+    gs.manual_seed(1)
+    sample = torch.randperm(N, generator=gs)[:32].sort().values.cuda()
+    want, min_gap, hop = sc.mutual_sets(Y, 0, N, sample, k)
+    assert sc.compare_neighbour_sets(lat._nbr[sample], want) == 0
+    assert hop > 200
+    psi = Y[:32].mean(dim=0)
+    psi = psi / psi.norm()
+    lat.set_query(psi.cpu().numpy())
+    st = lat.settle(max_iters=12, tol=1e-3)
+    assert st["res"] <= 1e-3
+    rows = (1000 + 3907 * torch.arange(256, device="cuda")).clamp_(max=N - 1)
+    r = sc.operator_residual_rows(rows, lambda i: lat._U[i], lambda i: lat._Y[i], lambda i: lat._Y[i], lat._nbr,
+                                  lat._W, psi, (lat.lamG, lat.lamC, lat.lamQ), settle=True)
+    est = float(torch.sqrt((r * r).sum(dim=0) * (N / r.shape[0])).max().item())
+    floor = 2.0 * 1.19e-7 * 7.0 * float(lat._U.double().pow(2).sum(dim=0).max().sqrt().item())
+    assert est <= 2.0 * (1e-3 + floor)

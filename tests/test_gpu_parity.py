@@ -591,3 +591,25 @@ def test_sparse_state_format_roundtrip(api, tmp_path):
     bs = api.OscillinkLattice.from_state(st_s)
     assert np.array_equal(bd._nbr.cpu().numpy(), bs._nbr.cpu().numpy())
     np.testing.assert_allclose(bd._W.cpu().numpy(), bs._W.cpu().numpy(), rtol=6e-7, atol=0)
+
+
+@pytest.mark.parametrize("name", ["perf_400", "quickstart_120", "gates_300"])
+def test_receipt_dynamics_match_reference(api, name, monkeypatch):
+    """OSCILLINK_RECEIPT_DYNAMICS=1 (lattice.py:825-927): temperature, step deltaH, edge flows and the BFS
+    radius of the first settle against the real reference (oracle/make_golden_dynamics.py)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dynamics.json")) as f:
+        ref = json.load(f)[name]
+    monkeypatch.setenv("OSCILLINK_RECEIPT_DYNAMICS", "1")
+    c = cases.build(name)
+    lat = _make(api, c)
+    lat.settle(**c["settle_kw"])
+    dyn = lat.receipt()["meta"]["dynamics"]
+    for key in ("temperature", "step_deltaH", "flow_total", "move2_mean", "move2_max"):
+        assert rel(dyn[key], ref[key]) < TOL, key
+    assert rel(dyn["viscosity_step"], ref["viscosity_step"]) < TOL
+    assert dyn["radius"] == ref["radius"]
+    assert [e["edge"] for e in dyn["top_flows"]] == [e["edge"] for e in ref["top_flows"]]
+    np.testing.assert_allclose([e["flow"] for e in dyn["top_flows"]], [e["flow"] for e in ref["top_flows"]], rtol=TOL)
