@@ -627,8 +627,8 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="both", worl
         V = n_loc * Dl * 4.0
         kms = {
             "pcg_spmm": t_of(lambda: kf.spmm(p_all)),
-            "pcg_update": t_of(lambda: kf.update(ones, ones)),
-            "pcg_pupdate": t_of(lambda: kf.pupdate(ones, ones)),
+            "pcg_update": t_of(lambda: kf.update(ones, ones, with_x=False)),
+            "pcg_pupdate_x": t_of(lambda: kf.pupdate_x(ones, ones, ones)),
         }
         halo = None
         if world > 1 and part == "rows":
@@ -651,12 +651,14 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="both", worl
         del p_all
         alg = {  # algorithmic bytes per launch
             "pcg_spmm": (nnz_loc / max(n_loc, 1) + 2.0) * V + 8.0 * nnz_loc,
-            "pcg_update": 6.0 * V,
-            "pcg_pupdate": 3.0 * V,
+            "pcg_update": 3.0 * V,     # r, Ap -> r (+ the column dots)
+            "pcg_pupdate_x": 5.0 * V,  # p, x, r -> p, x: the x update rides with the p update
         }
         gbs = {n: alg[n] / (kms[n] / 1000.0) / 1e9 for n in alg}
         iters = int(st["iters"])
-        solve_bytes = (iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"] + (iters - 1) * alg["pcg_pupdate"] + 4.0 * V
+        # the last iteration updates x alone (p, x -> x: 3 V); setup writes x0, b, r, p (4 V)
+        solve_bytes = ((iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"]
+                       + (iters - 1) * alg["pcg_pupdate_x"] + 3.0 * V + 4.0 * V)
         roof = {"kernel": "pcg_spmm_kernel", "bound": "hbm", "achieved": gbs["pcg_spmm"], "peak": peak,
                 "unit": "GB/s", "frac": gbs["pcg_spmm"] / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kms, "kernel_gbs": gbs,

@@ -268,7 +268,8 @@ int osc_pcg_reduce(const double* part, int32_t n_blocks, int32_t D, float* out, 
                    void* stream);
 
 /* x += alpha p; r -= alpha Ap; partial rr, partial rz' (solver.py:26-28,32-33);
- * alpha_c = rz_c/(pap_c + 1e-18) */
+ * alpha_c = rz_c/(pap_c + 1e-18).  X_loc == NULL: r and the partials only -- x is then updated by
+ * osc_pcg_pupdate_x (what osc_pcg_solve / osc_dist_pcg_solve do: one vector stream less per iteration). */
 int osc_pcg_update(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
                    int32_t jacobi, const float* gates_loc, const float* rz, const float* pap,
                    const float* P_loc, const float* AP_loc, float* X_loc, float* R_loc,
@@ -278,6 +279,14 @@ int osc_pcg_update(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t 
 int osc_pcg_pupdate(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
                     int32_t jacobi, const float* gates_loc, const float* rz_new, const float* rz_old,
                     const float* R_loc, float* P_loc, void* stream);
+
+/* x += alpha p (solver.py:25, alpha from rz_old / pap of the iteration just tested) and, unless `last`,
+ * p = z + beta p (solver.py:33-35) in one pass over p.  Same operations on the same operands as
+ * osc_pcg_update(X) + osc_pcg_pupdate: the iterates are bit-identical. */
+int osc_pcg_pupdate_x(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                      int32_t jacobi, const float* gates_loc, const float* rz_new, const float* rz_old,
+                      const float* pap, const float* R_loc, float* P_loc, float* X_loc, int32_t last,
+                      void* stream);
 
 /* Full single-GPU solve.  X receives the solution ([N][D]); *h_iters / *h_res the
  * iteration count and last max-column residual (never fails on non-convergence). */

@@ -118,6 +118,8 @@ PROTOTYPES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osc_pcg_pupdate": (C.c_int, [P(PcgDims), P(Params), c_i32, c_f32, c_i32, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osc_pcg_pupdate_x": (C.c_int, [P(PcgDims), P(Params), c_i32, c_f32, c_i32, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p]),
     "osc_pcg_solve": (C.c_int, [P(Graph), P(Chain), P(Params), c_i32, c_f32, c_i32, c_f32, c_i32, c_f64,
                                 c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, P(c_i32),
                                 P(c_f32), c_void_p, c_size_t, c_void_p]),

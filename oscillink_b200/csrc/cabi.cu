@@ -601,7 +601,8 @@ int osc_pcg_update(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t 
                    int32_t jacobi, const float* gates_loc, const float* rz, const float* pap,
                    const float* P_loc, const float* AP_loc, float* X_loc, float* R_loc,
                    double* part_rr, double* part_rz, void* stream) {
-  OSC_REQUIRE(dims && prm && rz && pap && P_loc && AP_loc && X_loc && R_loc && part_rr && part_rz,
+  // X_loc == NULL: r only -- the x update then belongs to osc_pcg_pupdate_x
+  OSC_REQUIRE(dims && prm && rz && pap && P_loc && AP_loc && R_loc && part_rr && part_rz,
               "pcg_update: NULL argument");
   return pcg_update(dims, prm, mode, dt, jacobi, gates_loc, rz, pap, P_loc, AP_loc, X_loc, R_loc,
                     part_rr, part_rz, (cudaStream_t)stream);
@@ -613,6 +614,15 @@ int osc_pcg_pupdate(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t
   OSC_REQUIRE(dims && prm && rz_new && rz_old && R_loc && P_loc, "pcg_pupdate: NULL argument");
   return pcg_pupdate(dims, prm, mode, dt, jacobi, gates_loc, rz_new, rz_old, R_loc, P_loc,
                      (cudaStream_t)stream);
+}
+
+int osc_pcg_pupdate_x(const osc_pcg_dims_t* dims, const osc_params_t* prm, int32_t mode, float dt,
+                      int32_t jacobi, const float* gates_loc, const float* rz_new, const float* rz_old,
+                      const float* pap, const float* R_loc, float* P_loc, float* X_loc, int32_t last,
+                      void* stream) {
+  OSC_REQUIRE(dims && prm && rz_new && rz_old && pap && R_loc && P_loc && X_loc, "pcg_pupdate_x: NULL argument");
+  return pcg_pupdate_x(dims, prm, mode, dt, jacobi, gates_loc, rz_new, rz_old, pap, R_loc, P_loc, X_loc, nullptr,
+                       0, last, (cudaStream_t)stream);
 }
 
 int osc_pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t* prm, int32_t mode,

@@ -402,6 +402,7 @@ int dist_pcg_solve(const osc_dist_t* ds, const osc_graph_t* g, const osc_chain_t
 
   // ---- iterations.  lag: how many iterations the host runs ahead of the device-side verdict
   const int lag = gather_mode(ds) ? 0 : 1;
+  const bool fuse_x = pcg_fuse_x();
   PcgCtl h{0, 0, __builtin_nanf(""), 0};
   int it = 0;
   for (it = 1; it <= max_iters; ++it) {
@@ -412,8 +413,8 @@ int dist_pcg_solve(const osc_dist_t* ds, const osc_graph_t* g, const osc_chain_t
       return rc;
     if ((rc = pcg_reduce(b.part_a, d.n_blocks, D, b.pap, nullptr, nullptr, st, done))) return rc;
     if (multi && rows) OSC_NCCL(api, api->AllReduce(b.pap, b.pap, (size_t)D, ncclFloat, ncclSum, comm, st));
-    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, b.pap, b.P, b.AP, X, b.R, b.part_a, b.part_b, st,
-                         done)))
+    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, b.pap, b.P, b.AP, fuse_x ? nullptr : X, b.R, b.part_a,
+                         b.part_b, st, done)))
       return rc;
     if ((rc = pcg_reduce(b.part_a, d.n_blocks, D, rr, b.d_res, nullptr, st, done))) return rc;
     if ((rc = pcg_reduce(b.part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st, done))) return rc;
@@ -425,12 +426,16 @@ int dist_pcg_solve(const osc_dist_t* ds, const osc_graph_t* g, const osc_chain_t
       if ((rc = pcg_decide(b.ctl, nullptr, b.d_res, D, tol, it, max_iters, st))) return rc;
     }
     if ((rc = poll->record(it, b.ctl, st))) return rc;
+    // x += alpha p (always part of this iteration) rides with p = z + beta p (skipped by the last one)
+    if (fuse_x &&
+        (rc = pcg_pupdate_x(&d, prm, mode, dt, jacobi, gates, rz_new, rz, b.pap, b.R, b.P, X, b.ctl, it, 0, st)))
+      return rc;
     if (it > lag) {
       if ((rc = poll->wait(it - lag, &h))) return rc;
       if (h.done) break;
     }
     if (it == max_iters) break;
-    if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, b.R, b.P, st, done))) return rc;
+    if (!fuse_x && (rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, b.R, b.P, st, done))) return rc;
     rz = rz_new;
   }
   if (it > max_iters) it = max_iters;

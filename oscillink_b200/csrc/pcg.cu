@@ -352,8 +352,9 @@ pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __rest
         const int64_t i = c0 + lr;
         const int64_t gi = dm.row0 + i;
         const float* own_p = vec + (local_ids ? i : gi) * dm.D + co;
-        float own[VEC], s[VEC];
+        float own[VEC], s[VEC], bv[VEC];
         ldv<VEC>(own_p, own);
+        if constexpr (RES0) ldv<VEC>(out + i * dm.D + co, bv);  // the right-hand side travels with the gathers
 #pragma unroll
         for (int v = 0; v < VEC; ++v) s[v] = 0.f;
         const int n = dgs[lr];
@@ -417,8 +418,7 @@ pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __rest
           }
         }
         if constexpr (RES0) {
-          float bv[VEC], r[VEC], z[VEC];
-          ldv<VEC>(out + i * dm.D + co, bv);
+          float r[VEC], z[VEC];
           const float md = md_diag(c, b);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
@@ -442,8 +442,10 @@ pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __rest
 }
 
 // ---------------------------------------------------------------- x, r update + partial rr, rz'
-template <int VEC>
-__global__ void __launch_bounds__(256)
+// (256, 3): <= 80 registers, i.e. four 192-thread blocks per SM -- the kernel is bound by the bytes it keeps
+// in flight (ncu: 124 registers / 12 warps per SM left it at 5.2 of 6.5 TB/s)
+template <int VEC, bool WITH_X>
+__global__ void __launch_bounds__(256, 3)
 pcg_update_kernel(Dims dm, Coef c, const float* __restrict__ gates, const float* __restrict__ rz,
                   const float* __restrict__ pap, const float* __restrict__ P,
                   const float* __restrict__ AP, float* __restrict__ X, float* __restrict__ R,
@@ -465,23 +467,54 @@ pcg_update_kernel(Dims dm, Coef c, const float* __restrict__ gates, const float*
     float alpha[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) alpha[v] = __fdiv_rn(rz[co + v], pap[co + v] + 1e-18f);
-    for (int64_t i = r_beg + threadIdx.y; i < r_end; i += blockDim.y) {
+    int64_t i = r_beg + threadIdx.y;
+    if constexpr (!WITH_X) {
+      // r only: two loads per row do not cover the HBM latency -- two rows per trip (four spill at 80 registers)
+      constexpr int U = 2;
+      for (; i + (U - 1) * (int64_t)blockDim.y < r_end; i += U * (int64_t)blockDim.y) {
+        float ap[U][VEC], r[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t o = (i + u * (int64_t)blockDim.y) * dm.D + co;
+          ldv<VEC>(AP + o, ap[u]);
+          ldv<VEC>(R + o, r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t iu = i + u * (int64_t)blockDim.y;
+          const float md = md_diag(c, gates ? gates[iu] : 1.0f);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            r[u][v] = __fsub_rn(r[u][v], __fmul_rn(ap[u][v], alpha[v]));
+            const float z = precond(c, r[u][v], md);
+            arr[v] += (double)r[u][v] * (double)r[u][v];
+            arz[v] += (double)r[u][v] * (double)z;
+          }
+          stv<VEC>(R + iu * dm.D + co, r[u]);
+        }
+      }
+    }
+    for (; i < r_end; i += blockDim.y) {
       const int64_t o = i * dm.D + co;
-      float p[VEC], ap[VEC], x[VEC], r[VEC];
-      ldv<VEC>(P + o, p);
+      float ap[VEC], r[VEC];
       ldv<VEC>(AP + o, ap);
-      ldv<VEC>(X + o, x);
       ldv<VEC>(R + o, r);
+      if constexpr (WITH_X) {  // otherwise the x update rides with the p update (pcg_pupdate_x_kernel)
+        float p[VEC], x[VEC];
+        ldv<VEC>(P + o, p);
+        ldv<VEC>(X + o, x);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[v] = __fadd_rn(x[v], __fmul_rn(p[v], alpha[v]));
+        stv<VEC>(X + o, x);
+      }
       const float md = md_diag(c, gates ? gates[i] : 1.0f);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        x[v] = __fadd_rn(x[v], __fmul_rn(p[v], alpha[v]));
         r[v] = __fsub_rn(r[v], __fmul_rn(ap[v], alpha[v]));
         const float z = precond(c, r[v], md);
         arr[v] += (double)r[v] * (double)r[v];
         arz[v] += (double)r[v] * (double)z;
       }
-      stv<VEC>(X + o, x);
       stv<VEC>(R + o, r);
     }
   }
@@ -514,6 +547,64 @@ __global__ void pcg_pupdate_kernel(Dims dm, Coef c, const float* __restrict__ ga
       p[v] = __fadd_rn(precond(c, r[v], md), __fmul_rn(p[v], beta));
     }
     stv<VEC>(P + o, p);
+  }
+}
+
+// x += alpha p and p = z + beta p in ONE pass over p (solver.py:25,33-35): the x update of an iteration does
+// not feed its stop test, so it can wait for the pass that rewrites p anyway -- 8 instead of 9 vector streams
+// per iteration next to the SpMM.  Same operations on the same operands, so x is bit-identical.  The kernel
+// runs after the iteration's verdict: finished in THIS iteration -> x only; finished earlier -> nothing.
+template <int VEC>
+__global__ void pcg_pupdate_x_kernel(Dims dm, Coef c, const float* __restrict__ gates,
+                                     const float* __restrict__ rz_new, const float* __restrict__ rz_old,
+                                     const float* __restrict__ pap, const float* __restrict__ R,
+                                     float* __restrict__ P, float* __restrict__ X, const PcgCtl* __restrict__ ctl,
+                                     int it, int x_only) {
+  bool fin = x_only != 0;  // ctl == NULL: the host knows whether this was the last iteration
+  if (ctl != nullptr) {
+    fin = ctl->done != 0;
+    if (fin && ctl->iters != it) return;
+  }
+  const int CG = dm.D / VEC;
+  const int64_t total = dm.n_local * CG;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;  // two chunks per trip: six loads in flight per thread (the kernel is latency bound)
+  for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += U * stride) {
+    float p[U][VEC], x[U][VEC], r[U][VEC];
+    int64_t row[U], off[U];
+    int co[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * stride;
+      ok[u] = e < total;
+      row[u] = ok[u] ? e / CG : 0;
+      co[u] = ok[u] ? (int)(e - row[u] * CG) * VEC : 0;
+      off[u] = row[u] * dm.D + co[u];
+      if (ok[u]) {
+        ldv<VEC>(P + off[u], p[u]);
+        ldv<VEC>(X + off[u], x[u]);
+        if (!fin) ldv<VEC>(R + off[u], r[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float alpha = __fdiv_rn(rz_old[co[u] + v], pap[co[u] + v] + 1e-18f);
+        x[u][v] = __fadd_rn(x[u][v], __fmul_rn(p[u][v], alpha));
+      }
+      stv<VEC>(X + off[u], x[u]);
+      if (fin) continue;
+      const float md = md_diag(c, gates ? gates[row[u]] : 1.0f);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float beta = __fdiv_rn(rz_new[co[u] + v], rz_old[co[u] + v] + 1e-18f);
+        p[u][v] = __fadd_rn(precond(c, r[u][v], md), __fmul_rn(p[u][v], beta));
+      }
+      stv<VEC>(P + off[u], p[u]);
+    }
   }
 }
 
@@ -794,8 +885,13 @@ int pcg_update(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float
   Coef c = make_coef(prm, mode, dt, jacobi);
   const size_t smem = (size_t)blk.x * blk.y * vec * sizeof(double);
   const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
-  OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC><<<grid, blk, smem, st>>>(
-                            to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz, done);)
+  if (X != nullptr) {
+    OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC, true><<<grid, blk, smem, st>>>(
+                              to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz, done);)
+  } else {
+    OSC_VEC_DISPATCH(vec, pcg_update_kernel<VEC, false><<<grid, blk, smem, st>>>(
+                              to_dims(d), c, gates, rz, pap, P, AP, X, R, part_rr, part_rz, done);)
+  }
   OSC_LAUNCH_CHECK("pcg_update_kernel");
   return OSC_OK;
 }
@@ -812,6 +908,21 @@ int pcg_pupdate(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, floa
   OSC_VEC_DISPATCH(vec, pcg_pupdate_kernel<VEC><<<ew_grid(total), 256, 0, st>>>(
                             to_dims(d), c, gates, rz_new, rz_old, R, P, done);)
   OSC_LAUNCH_CHECK("pcg_pupdate_kernel");
+  return OSC_OK;
+}
+
+int pcg_pupdate_x(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int jacobi,
+                  const float* gates, const float* rz_new, const float* rz_old, const float* pap, const float* R,
+                  float* P, float* X, const PcgCtl* ctl, int it, int x_only, cudaStream_t st) {
+  if (d->n_local == 0) return OSC_OK;
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  Coef c = make_coef(prm, mode, dt, jacobi);
+  const int64_t total = d->n_local * (d->D / vec);
+  OSC_VEC_DISPATCH(vec, pcg_pupdate_x_kernel<VEC><<<ew_grid(total), 256, 0, st>>>(
+                            to_dims(d), c, gates, rz_new, rz_old, pap, R, P, X, ctl, it, x_only);)
+  OSC_LAUNCH_CHECK("pcg_pupdate_x_kernel");
   return OSC_OK;
 }
 
@@ -859,6 +970,12 @@ int launch_sum_doubles(const double* v, int D, double* total, cudaStream_t st) {
   sum_doubles_kernel<<<1, 1024, 0, st>>>(v, D, total);
   OSC_LAUNCH_CHECK("sum_doubles_kernel");
   return OSC_OK;
+}
+
+// dev switch: OSC_PCG_FUSE_X=0 runs x += alpha p inside the r update again (A/B of the deferred x update)
+bool pcg_fuse_x() {
+  const char* e = getenv("OSC_PCG_FUSE_X");
+  return !(e != nullptr && atoi(e) == 0);
 }
 
 // ---------------------------------------------------------------- lagged host poll of the control block
@@ -916,6 +1033,7 @@ static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_cha
   CtlPoll* poll = ctl_poll();
   if (poll == nullptr) return OSC_ERR_CUDA;
   const int* done = &ctl->done;
+  const bool fuse_x = pcg_fuse_x();
   int rc;
   OSC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PcgCtl), st));
   if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) return rc;
@@ -925,18 +1043,22 @@ static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_cha
   for (it = 1; it <= max_iters; ++it) {
     if ((rc = pcg_spmm_dot(&d, g, chain, prm, mode, dt, gates, P, AP, part_a, st, done))) return rc;
     if ((rc = pcg_reduce(part_a, d.n_blocks, D, pap, nullptr, nullptr, st, done))) return rc;
-    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, X, R, part_a, part_b, st, done)))
+    if ((rc = pcg_update(&d, prm, mode, dt, jacobi, gates, rz, pap, P, AP, fuse_x ? nullptr : X, R, part_a, part_b,
+                         st, done)))
       return rc;
     if ((rc = pcg_reduce(part_a, d.n_blocks, D, rr, d_res, nullptr, st, done))) return rc;
     if ((rc = pcg_reduce(part_b, d.n_blocks, D, rz_new, nullptr, nullptr, st, done))) return rc;
     if ((rc = pcg_decide(ctl, nullptr, d_res, D, tol, it, max_iters, st))) return rc;
     if ((rc = poll->record(it, ctl, st))) return rc;
+    // x += alpha p always belongs to this iteration; p = z + beta p only if it was not the last
+    if (fuse_x && (rc = pcg_pupdate_x(&d, prm, mode, dt, jacobi, gates, rz_new, rz, pap, R, P, X, ctl, it, 0, st)))
+      return rc;
     if (it > 1) {  // the previous iteration's verdict has landed (or lands while this one runs)
       if ((rc = poll->wait(it - 1, &h))) return rc;
       if (h.done) break;
     }
     if (it == max_iters) break;
-    if ((rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st, done))) return rc;
+    if (!fuse_x && (rc = pcg_pupdate(&d, prm, mode, dt, jacobi, gates, rz_new, rz, R, P, st, done))) return rc;
     float* t = rz;
     rz = rz_new;
     rz_new = t;

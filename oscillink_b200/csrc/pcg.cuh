@@ -60,6 +60,11 @@ int pcg_update(const osc_pcg_dims_t*, const osc_params_t*, int mode, float dt, i
 int pcg_pupdate(const osc_pcg_dims_t*, const osc_params_t*, int mode, float dt, int jacobi,
                 const float* gates, const float* rz_new, const float* rz_old, const float* R, float* P,
                 cudaStream_t, const int* done = nullptr);
+bool pcg_fuse_x();
+// x += alpha p fused with p = z + beta p (after the iteration's verdict; see pcg_pupdate_x_kernel)
+int pcg_pupdate_x(const osc_pcg_dims_t*, const osc_params_t*, int mode, float dt, int jacobi, const float* gates,
+                  const float* rz_new, const float* rz_old, const float* pap, const float* R, float* P, float* X,
+                  const PcgCtl* ctl, int it, int x_only, cudaStream_t st);
 // stop test on the device: res = max_c sqrt(rr_c) from the column sums rr[D] (or, if rr == nullptr, the
 // already reduced *d_res); records {iters = it, res}; sets done when res <= tol or it >= max_iters
 int pcg_decide(PcgCtl* ctl, const float* rr, const float* d_res, int D, double tol, int it, int max_iters,

@@ -224,12 +224,20 @@ class _NativeKernels:
                         "osc_pcg_reduce")
         return self.out[which]
 
-    def update(self, rz, pap):
+    def update(self, rz, pap, with_x: bool = True):
         self.cabi.check(self.lib.osc_pcg_update(
             C.byref(self.dims), C.byref(self.prm), self.mode_id, self.dt, self.jacobi,
             self.gates.data_ptr(), rz.data_ptr(), pap.data_ptr(), self.P.data_ptr(), self.AP.data_ptr(),
-            self.X.data_ptr(), self.R.data_ptr(), self.parts["rr"].data_ptr(),
+            self.X.data_ptr() if with_x else None, self.R.data_ptr(), self.parts["rr"].data_ptr(),
             self.parts["rz_new"].data_ptr(), self._st()), "osc_pcg_update")
+
+    def pupdate_x(self, rz_new, rz_old, pap, last: bool = False):
+        """x += alpha p fused with p = z + beta p: the pair osc_pcg_solve / osc_dist_pcg_solve run (after
+        update(with_x=False)); exposed for per-kernel timing."""
+        self.cabi.check(self.lib.osc_pcg_pupdate_x(
+            C.byref(self.dims), C.byref(self.prm), self.mode_id, self.dt, self.jacobi,
+            self.gates.data_ptr(), rz_new.data_ptr(), rz_old.data_ptr(), pap.data_ptr(), self.R.data_ptr(),
+            self.P.data_ptr(), self.X.data_ptr(), 1 if last else 0, self._st()), "osc_pcg_pupdate_x")
 
     def pupdate(self, rz_new, rz_old):
         self.cabi.check(self.lib.osc_pcg_pupdate(

@@ -613,3 +613,31 @@ def test_receipt_dynamics_match_reference(api, name, monkeypatch):
     assert dyn["radius"] == ref["radius"]
     assert [e["edge"] for e in dyn["top_flows"]] == [e["edge"] for e in ref["top_flows"]]
     np.testing.assert_allclose([e["flow"] for e in dyn["top_flows"]], [e["flow"] for e in ref["top_flows"]], rtol=TOL)
+
+
+def test_deferred_x_update_is_bit_identical(monkeypatch):
+    """osc_pcg_solve applies x += alpha p in the pass that rewrites p (pcg_pupdate_x_kernel) instead of the r
+    update (solver.py:25 next to :26): the same operations on the same operands, so settle and U* must not
+    change by a single bit -- converged (stops in the middle) and capped (max_iters reached) alike."""
+    import oscillink_b200 as api
+
+    rs = np.random.RandomState(21)
+    Y = rs.randn(3000, 96).astype(np.float32)
+    psi = Y[:32].mean(axis=0)
+    psi = (psi / np.linalg.norm(psi)).astype(np.float32)
+    out = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("OSC_PCG_FUSE_X", fuse)
+        lat = api.OscillinkLattice(Y, kneighbors=8, deterministic_k=True)
+        lat.set_query(psi)
+        lat.add_chain([3, 9, 27, 81], lamP=0.2)
+        capped = lat.settle(max_iters=2, tol=1e-9)
+        U2 = lat.U.copy()
+        st = lat.settle(max_iters=12, tol=1e-3)
+        out[fuse] = (capped["iters"], capped["res"], U2, st["iters"], st["res"], lat.U.copy(), lat.solve_Ustar().copy())
+    a, b = out["0"], out["1"]
+    assert a[0] == b[0] == 2 and a[1] == b[1]
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3] and a[4] == b[4]
+    assert np.array_equal(a[5], b[5])
+    assert np.array_equal(a[6], b[6])
