@@ -249,12 +249,20 @@ __device__ __forceinline__ void pk_chunk(int (&key)[KC], float (&v)[32], int c0,
 #pragma unroll
   for (int i = 0; i < 32; ++i) buf[i * 32 + lane] = v[i];
   __syncwarp();
-  while (__any_sync(0xffffffffu, mask != 0)) {
-    if (mask != 0) {
-      const int e = __ffs(mask) - 1;
-      mask &= mask - 1;
-      pk_insert<KC>(key, pk_key(buf[e * 32 + lane], c0 + e));
-    }
+  // Insertion rounds, software-pipelined: the next hit of every lane (bit scan -> LDS -> key packing, a
+  // ~80-cycle dependent chain) is fetched while the min/max network of the current one runs.  A lane without
+  // a hit inserts INT_MIN, which the network leaves unchanged, so the loop body is branch-free.
+  auto next_key = [&]() -> int {
+    if (mask == 0) return INT_MIN;
+    const int e = __ffs(mask) - 1;
+    mask &= mask - 1;
+    return pk_key(buf[e * 32 + lane], c0 + e);
+  };
+  int cur = next_key();
+  while (__any_sync(0xffffffffu, cur != INT_MIN)) {
+    const int nxt = next_key();
+    pk_insert<KC>(key, cur);
+    cur = nxt;
   }
   __syncwarp();
 }
