@@ -685,6 +685,66 @@ int launch_knn_simt(const float* Yq, const float* Yall, int64_t batch, int64_t n
   return OSC_OK;
 }
 
+// kc == 16: one HALF warp per row, everything in registers.  The warp-per-row kernel above keeps ~10 of 32
+// lanes busy and goes through shared memory for every comparison (ncu: 409 warp instructions per row, issue
+// slots 85 % busy -- instruction bound); here lane c of a half warp holds candidate c and reads the others
+// with width-16 shuffles.  Same ranking rule, same outputs.
+__global__ void __launch_bounds__(256)
+knn_rescore_rank16_kernel(int64_t N, const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_sim,
+                          int k, float eps, const float* __restrict__ S, int32_t* __restrict__ top_idx,
+                          float* __restrict__ top_sim, float* __restrict__ gap, int64_t* __restrict__ flagged,
+                          int* __restrict__ n_flagged) {
+  constexpr int KC = 16;
+  const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+  const int64_t b = blockIdx.y;
+  const int64_t r = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
+  const bool row_ok = r < N;  // no early return: the shuffles below are warp-wide
+  const int64_t base = (b * N + (row_ok ? r : 0)) * KC;
+  const int j = row_ok ? cand_idx[base + hl] : -1;
+  const float a = row_ok ? cand_sim[base + hl] : -INFINITY;
+  // candidates that can still be among the k best: approximate score within 2 eps of the (k+1)-th (the list
+  // is sorted by approximate score, so they form a prefix); at least k + 1 of them
+  const float a_k = __shfl_sync(0xffffffffu, a, k, 16);
+  const unsigned m = (__ballot_sync(0xffffffffu, a >= a_k - 2.0f * eps) >> (16 * half)) & 0xffffu;
+  int n_keep = __popc(m);
+  n_keep = n_keep < k + 1 ? k + 1 : n_keep;
+  const bool kept = row_ok && hl < n_keep && j >= 0;
+  float s = -INFINITY;
+  if (kept) {
+    s = S[base + hl];
+    if (s != s) s = S[(b * N + j) * KC + (__float_as_int(s) & 0xff)];  // the pair was scored by row j
+  }
+  int rank = 0;
+#pragma unroll
+  for (int c2 = 0; c2 < KC; ++c2) {
+    const float s2 = __shfl_sync(0xffffffffu, s, c2, 16);
+    const int j2 = __shfl_sync(0xffffffffu, kept ? j : -1, c2, 16);
+    if (j2 >= 0 && c2 != hl && better(s2, j2, s, j)) ++rank;
+  }
+  float kth = INFINITY, nxt = -INFINITY;
+  if (kept) {
+    const int64_t o = (b * N + r) * k;
+    if (rank < k) {
+      top_idx[o + rank] = j;
+      top_sim[o + rank] = s;
+    }
+    if (rank == k - 1) kth = s;
+    if (rank == k) nxt = s;
+  }
+  float amin = (row_ok && j >= 0) ? a : INFINITY;
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {
+    kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, off, 16));
+    nxt = fmaxf(nxt, __shfl_xor_sync(0xffffffffu, nxt, off, 16));
+    amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off, 16));
+  }
+  if (row_ok && hl == 0) {
+    if (gap != nullptr) gap[b * N + r] = (nxt == -INFINITY) ? INFINITY : kth - nxt;
+    if (flagged != nullptr && (int64_t)KC < N - 1 && (kth == INFINITY || amin + eps >= kth))
+      flagged[atomicAdd(n_flagged, 1)] = b * N + r;  // completeness check, as in knn_rescore_kernel
+  }
+}
+
 // cand_sim / flagged / n_flagged may be NULL (no completeness check, the plain osc_knn_rescore).
 // With them: rows whose candidate list cannot be proven complete are recomputed exhaustively.
 int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_rows, int64_t row0,
@@ -716,8 +776,19 @@ int launch_rescore(const float* Yq, const float* Yall, int64_t batch, int64_t n_
     else
       knn_rescore_owned_kernel<32><<<grid, warps * 32, sm_a, st>>>(Yall, N, D, cand_idx, cand_sim, k, eps, dedup_S);
     OSC_LAUNCH_CHECK("knn_rescore_owned_kernel");
-    knn_rescore_rank_kernel<<<grid, warps * 32, smem, st>>>(N, cand_idx, cand_sim, kc, k, eps, dedup_S, top_idx,
-                                                            top_sim, gap, flagged, n_flagged);
+    bool rank16 = kc == 16 && k < 16;
+    {
+      const char* e = getenv("OSC_RESCORE_RANK16");  // dev-only A/B switch
+      if (e && atoi(e) == 0) rank16 = false;
+    }
+    if (rank16) {
+      dim3 grid2((unsigned)((n_rows + 2 * warps - 1) / (2 * warps)), (unsigned)batch);
+      knn_rescore_rank16_kernel<<<grid2, warps * 32, 0, st>>>(N, cand_idx, cand_sim, k, eps, dedup_S, top_idx, top_sim,
+                                                            gap, flagged, n_flagged);
+    } else {
+      knn_rescore_rank_kernel<<<grid, warps * 32, smem, st>>>(N, cand_idx, cand_sim, kc, k, eps, dedup_S, top_idx,
+                                                              top_sim, gap, flagged, n_flagged);
+    }
     OSC_LAUNCH_CHECK("knn_rescore_rank_kernel");
   }
   auto fn = knn_rescore_kernel<0>;
