@@ -285,6 +285,30 @@ def test_duplicate_free_rescoring_is_bit_identical(N, D, k, monkeypatch):
     assert res[0][4] == res[1][4]
 
 
+@pytest.mark.parametrize("N,D,k,switch", [(1200, 384, 8, "OSC_ASSEMBLE_REG"), (500, 64, 4, "OSC_ASSEMBLE_REG"),
+                                          (300, 36, 12, "OSC_ASSEMBLE_REG"), (1200, 384, 8, "OSC_RESCORE_RANK16"),
+                                          (700, 128, 5, "OSC_RESCORE_RANK16")])
+def test_register_resident_build_kernels_are_bit_identical(N, D, k, switch, monkeypatch):
+    """assemble_mutual_reg_kernel (k in 4/8/12/16: mutual filter with the lists in registers) against the generic
+    assemble_mutual_kernel, and knn_rescore_rank16_kernel (half a warp per row, shuffles) against the
+    shared-memory ranking pass: identical graphs, weights, degrees and gaps."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    Y, psi = _inputs(3, N, D, seed0=900)
+    Y[2, 11] = Y[2, 5]
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv(switch, flag)
+        bl = BatchedLattices(Y, kneighbors=k)
+        torch.cuda.synchronize()
+        res.append((bl.nbr.cpu().numpy(), bl.A.cpu().numpy(), bl.W.cpu().numpy(), bl.gap.cpu().numpy(),
+                    bl.deg.cpu().numpy(), bl.sqrt_deg.cpu().numpy()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+
+
 def test_settle_host_batch_returns_the_settled_state():
     """settle_host_batch(U_host=...): the settled U of every lattice comes back through a third stream."""
     import torch
