@@ -594,7 +594,8 @@ static BatchedFn ms_pick_t(int64_t N, int kq, int* threads) {
 
 // The multi-shift kernel that serves (N, kq), its block size and dynamic shared memory; nullptr if none.
 // variant (dev A/B): 0 = auto, 1 = T x 2 rows + shared-memory graph, 2 = T x 4 rows + shared-memory graph,
-// 3 = T x 5 rows + graph in registers, 4 = T x 4 rows, x_u / x_s / p_s in tensor memory, two CTAs per SM
+// 3 = T x 5 rows + graph in registers, 4 = T x 4 rows, x_u / x_s / p_s in tensor memory, two CTAs per SM,
+// 5 = as 4 with T x 5 rows
 BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* smem_dyn, bool* two_ctas) {
   *two_ctas = false;
   if (kq < 1 || kq > 4 || N < 1) return nullptr;
@@ -607,6 +608,17 @@ BatchedFn batched_ms_pick(int64_t N, int kq, int variant, int* threads, size_t* 
     f = ms_pick_t<4, false, 320, true>(N, kq, threads);
     if (f != nullptr) {
       *smem_dyn = (size_t)*threads * 4 * (kq * (16 + 8) + 16);  // graph image + ONE Y-slab buffer
+      *two_ctas = true;
+      return f;
+    }
+  }
+  // dev: as 4 with 5 rows per thread (256 threads, 128 registers, 16 warps per SM): 13.20 vs 13.36 ms at
+  // B = 1440.  With the register room the p^s update was folded into the x update once more (one tensor-memory
+  // visit per row and iteration, zeta / b^s re-read from shared memory): 13.37 ms -- not kept.
+  if (variant == 5 && kq <= 2) {
+    f = ms_pick_t<5, false, 256, true>(N, kq, threads);
+    if (f != nullptr) {
+      *smem_dyn = (size_t)*threads * 5 * (kq * (16 + 8) + 16);
       *two_ctas = true;
       return f;
     }
