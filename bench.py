@@ -656,9 +656,10 @@ def measure_large(N, D, k, *, steps, warmup, chain_len=0, partition="both", worl
         }
         gbs = {n: alg[n] / (kms[n] / 1000.0) / 1e9 for n in alg}
         iters = int(st["iters"])
-        # the last iteration updates x alone (p, x -> x: 3 V); setup writes x0, b, r, p (4 V)
+        # the last iteration updates x alone (p, x -> x: 3 V); the first residual forms the right-hand side in
+        # place (no setup pass): next to a SpMM's bytes it reads the Y row and writes z0 (2 V)
         solve_bytes = ((iters + 1) * alg["pcg_spmm"] + iters * alg["pcg_update"]
-                       + (iters - 1) * alg["pcg_pupdate_x"] + 3.0 * V + 4.0 * V)
+                       + (iters - 1) * alg["pcg_pupdate_x"] + 3.0 * V + 2.0 * V)
         roof = {"kernel": "pcg_spmm_kernel", "bound": "hbm", "achieved": gbs["pcg_spmm"], "peak": peak,
                 "unit": "GB/s", "frac": gbs["pcg_spmm"] / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kms, "kernel_gbs": gbs,

@@ -377,8 +377,15 @@ int dist_pcg_solve(const osc_dist_t* ds, const osc_graph_t* g, const osc_chain_t
   if (gather_mode(ds) && n_loc < ds->shard)  // the pad rows of the last rank travel with the all-gather
     OSC_CUDA(cudaMemsetAsync(b.P + nd, 0, (size_t)(ds->shard - n_loc) * D * sizeof(float), st));
 
-  // x0 and right-hand side (lattice.py:171,184 / :245, :751-758)
-  if ((rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, b.R, st))) return rc;
+  // x0 and right-hand side (lattice.py:171,184 / :245, :751-758).  All rows local (one GPU, column slabs) and a
+  // start vector that is Y or U itself: no setup pass -- the first residual forms the right-hand side in place
+  // and gathers the start vector where it lies (pcg_solve does the same).
+  const bool settle = mode == OSC_MODE_SETTLE;
+  const float* x0 = (!settle || !warm) ? Y : U;
+  const bool fused = !(multi && rows) && max_iters >= 1 && ds->N > 0 && !(settle && warm && inertia > 0.f) &&
+                     pcg_fuse_x() && x0 != X && pcg_fused_init_ok(&d, &gl);
+  const InitSrc init{Y, U, psi, x0 == Y ? 1 : 0, x0 == U ? 1 : 0};
+  if (!fused && (rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, b.R, st))) return rc;
   if (max_iters < 1 || ds->N == 0) return OSC_OK;
 
   // ---- r0 = b - A x0 ; p0 = z0 ; rz
@@ -395,8 +402,10 @@ int dist_pcg_solve(const osc_dist_t* ds, const osc_graph_t* g, const osc_chain_t
     // (the all-reduce completes only after every rank has issued its own, i.e. finished pulling)
     if (pull_mode(ds) && nd) OSC_CUDA(cudaMemcpyAsync(b.P, b.AP, nd * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
-    vv = VecView{X, nullptr, 0, 0};
-    if ((rc = spmm_launch(true, &d, &gl, chain, prm, mode, dt, jacobi, gates, vv, b.R, b.P, b.part_a, st))) return rc;
+    vv = VecView{fused ? x0 : X, nullptr, 0, 0};
+    if ((rc = spmm_launch(true, &d, &gl, chain, prm, mode, dt, jacobi, gates, vv, b.R, b.P, b.part_a, st, nullptr,
+                          fused ? &init : nullptr)))
+      return rc;
     if ((rc = pcg_reduce(b.part_a, d.n_blocks, D, rz, nullptr, nullptr, st))) return rc;
   }
 
@@ -428,7 +437,8 @@ int dist_pcg_solve(const osc_dist_t* ds, const osc_graph_t* g, const osc_chain_t
     if ((rc = poll->record(it, b.ctl, st))) return rc;
     // x += alpha p (always part of this iteration) rides with p = z + beta p (skipped by the last one)
     if (fuse_x &&
-        (rc = pcg_pupdate_x(&d, prm, mode, dt, jacobi, gates, rz_new, rz, b.pap, b.R, b.P, X, b.ctl, it, 0, st)))
+        (rc = pcg_pupdate_x(&d, prm, mode, dt, jacobi, gates, rz_new, rz, b.pap, b.R, b.P, X, b.ctl, it, 0, st,
+                            (fused && it == 1) ? x0 : nullptr)))
       return rc;
     if (it > lag) {
       if ((rc = poll->wait(it - lag, &h))) return rc;

@@ -297,17 +297,23 @@ pcg_spmm_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restr
 // being gathered: one barrier per chunk instead of two, and the staging latency (a dependent global load in
 // front of every chunk) disappears behind the gathers.  Row addresses are formed at the point of use
 // (one 64-bit multiply-add per fetch) instead of being staged as pointers: 8 instead of 12 bytes per entry.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
 }
 
-template <int VEC, bool RES0>
+// RES0: 0 = A p and p.Ap; 1 = first residual, `out` holds the right-hand side on entry; 2 = first residual with
+// the right-hand side formed in place from Y, U and psi (the arithmetic of pcg_setup_kernel), gathered vector =
+// the start vector itself (Y or U): no setup pass, no x0 / b round trip through HBM (5 vector streams less).
+template <int VEC, int RES0>
 __global__ void __launch_bounds__(256)
 pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __restrict__ gates,
                  const float* __restrict__ vec, int local_ids, float* __restrict__ out,
                  float* __restrict__ Pout, double* __restrict__ part, int rch,
-                 const int* __restrict__ done) {
+                 const int* __restrict__ done, InitSrc src) {
   extern __shared__ double sh[];
   if (done != nullptr && *done != 0) return;
   const int CG = dm.D / VEC;
@@ -337,6 +343,12 @@ pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __rest
   double acc[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+  float psiv[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) psiv[v] = 0.f;
+  if constexpr (RES0 == 2) {
+    if (col_ok) ldv<VEC>(src.psi + co, psiv);
+  }
   if (r_beg < r_end) stage(0, r_beg, (int)min((int64_t)rch, r_end - r_beg));
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
@@ -354,7 +366,13 @@ pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __rest
         const float* own_p = vec + (local_ids ? i : gi) * dm.D + co;
         float own[VEC], s[VEC], bv[VEC];
         ldv<VEC>(own_p, own);
-        if constexpr (RES0) ldv<VEC>(out + i * dm.D + co, bv);  // the right-hand side travels with the gathers
+        if constexpr (RES0 == 1) ldv<VEC>(out + i * dm.D + co, bv);  // the right-hand side travels with the gathers
+        if constexpr (RES0 == 2) {
+          // a row of Y / U that is not the gathered vector itself is only PREFETCHED here (into L2) and loaded
+          // after the gathers: held in registers across them it costs 40 registers and half the resident warps
+          if (!src.y_is_x0) prefetch_l2(src.Y + i * dm.D + co);
+          if (!src.u_is_x0 && c.settle) prefetch_l2(src.U + i * dm.D + co);
+        }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) s[v] = 0.f;
         const int n = dgs[lr];
@@ -417,7 +435,21 @@ pcg_spmm2_kernel(Dims dm, Coef c, GraphView g, ChainView ch, const float* __rest
             for (int v = 0; v < VEC; ++v) o[v] -= offp * sp[v];
           }
         }
-        if constexpr (RES0) {
+        if constexpr (RES0 == 2) {  // pcg_setup_kernel's right-hand side, same operations in the same order
+          float yv[VEC], uv[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) yv[v] = uv[v] = own[v];
+          if (!src.y_is_x0) ldv<VEC>(src.Y + i * dm.D + co, yv);
+          if (!src.u_is_x0 && c.settle) ldv<VEC>(src.U + i * dm.D + co, uv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float y = yv[v];
+            const float u = uv[v];
+            const float rhs = __fadd_rn(__fmul_rn(c.lamG, y), __fmul_rn(c.lamQ, __fmul_rn(b, psiv[v])));
+            bv[v] = c.settle ? __fadd_rn(u, __fmul_rn(c.dt, rhs)) : rhs;
+          }
+        }
+        if constexpr (RES0 != 0) {
           float r[VEC], z[VEC];
           const float md = md_diag(c, b);
 #pragma unroll
@@ -559,7 +591,7 @@ __global__ void pcg_pupdate_x_kernel(Dims dm, Coef c, const float* __restrict__ 
                                      const float* __restrict__ rz_new, const float* __restrict__ rz_old,
                                      const float* __restrict__ pap, const float* __restrict__ R,
                                      float* __restrict__ P, float* __restrict__ X, const PcgCtl* __restrict__ ctl,
-                                     int it, int x_only) {
+                                     int it, int x_only, const float* __restrict__ Xsrc) {
   bool fin = x_only != 0;  // ctl == NULL: the host knows whether this was the last iteration
   if (ctl != nullptr) {
     fin = ctl->done != 0;
@@ -583,7 +615,7 @@ __global__ void pcg_pupdate_x_kernel(Dims dm, Coef c, const float* __restrict__ 
       off[u] = row[u] * dm.D + co[u];
       if (ok[u]) {
         ldv<VEC>(P + off[u], p[u]);
-        ldv<VEC>(X + off[u], x[u]);
+        ldv<VEC>(Xsrc + off[u], x[u]);  // X itself, or the start vector in the first iteration of a fused start
         if (!fin) ldv<VEC>(R + off[u], r[u]);
       }
     }
@@ -776,14 +808,38 @@ int pcg_max_ell_width(int D) {
   return (int)((kSpmmSmemMax - fixed) / 12);
 }
 
+// does the double-buffered kernel (one buffer holds the gathered vector) serve this launch?
+static bool spmm_two_buffer(const dim3& blk, int vec, int k, int rch, const VecView& vv, size_t* smem2) {
+  bool two = vv.peers == nullptr && vv.all != nullptr && rch >= 2;
+  static const int off = [] { const char* e = getenv("OSC_SPMM2"); return (e && atoi(e) == 0) ? 1 : 0; }();
+  if (off) two = false;  // dev-only A/B switch
+  // same bytes as the pointer staging: 2 buffers x rch x (8 k + 4) <= rch x (12 k + 4) + ... for k >= 1
+  *smem2 = (size_t)blk.x * blk.y * vec * sizeof(double) + 2 * (size_t)rch * ((size_t)k * 8 + 4);
+  return two && *smem2 <= kSpmmSmemMax;
+}
+
+// the fused first residual (InitSrc) exists in the double-buffered kernel only
+bool pcg_fused_init_ok(const osc_pcg_dims_t* d, const osc_graph_t* g) {
+  const char* e = getenv("OSC_PCG_FUSE_INIT");  // dev-only A/B switch (read per call: tests flip it)
+  if ((e && atoi(e) == 0) || d->n_local == 0) return false;
+  int vec;
+  dim3 blk;
+  block_shape(d->D, vec, blk);
+  const int rch = spmm_chunk_rows(blk, vec, g->k);
+  size_t smem2 = 0;
+  const float dummy = 0.f;
+  return rch != 0 && spmm_two_buffer(blk, vec, g->k, rch, VecView{&dummy, nullptr, 0, 0}, &smem2);
+}
+
 int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                 const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates, VecView vv,
-                float* out, float* Pout, double* part, cudaStream_t st, const int* done) {
+                float* out, float* Pout, double* part, cudaStream_t st, const int* done, const InitSrc* init) {
   if (d->n_local == 0) return OSC_OK;
   int vec;
   dim3 blk;
   block_shape(d->D, vec, blk);
-  if (!((vv.all == nullptr || aligned16(vv.all)) && aligned16(out) && (Pout == nullptr || aligned16(Pout)))) {
+  if (!((vv.all == nullptr || aligned16(vv.all)) && aligned16(out) && (Pout == nullptr || aligned16(Pout)) &&
+        (init == nullptr || (aligned16(init->Y) && aligned16(init->U) && aligned16(init->psi))))) {
     if (vec == 4) return fail(OSC_ERR_INVALID, "pcg: vectors must be 16-byte aligned when D % 4 == 0");
   }
   Coef c = make_coef(prm, mode, dt, jacobi);
@@ -791,33 +847,31 @@ int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g, const 
   if (rch == 0) return fail(OSC_ERR_UNSUPPORTED, "pcg: ELL width too large for the staged SpMM");
   const size_t smem = spmm_smem_bytes(blk, vec, g->k, rch);
   const dim3 grid((unsigned)d->n_blocks, (unsigned)((d->D / vec + (int)blk.x - 1) / (int)blk.x), 1);
-  // one buffer holds the gathered vector (everything but the fused-P2P view): double-buffered staging
-  bool two = vv.peers == nullptr && vv.all != nullptr && rch >= 2;
-  {
-    static const int off = [] { const char* e = getenv("OSC_SPMM2"); return (e && atoi(e) == 0) ? 1 : 0; }();
-    if (off) two = false;  // dev-only A/B switch
-  }
+  size_t smem2 = 0;
+  const bool two = spmm_two_buffer(blk, vec, g->k, rch, vv, &smem2);
+  if (init != nullptr && !(two && res0))
+    return fail(OSC_ERR_UNSUPPORTED, "pcg: fused first residual needs the double-buffered SpMM (pcg_fused_init_ok)");
   if (two) {
-    // same bytes as the pointer staging: 2 buffers x rch x (8 k + 4) <= rch x (12 k + 4) + ... for k >= 1
-    const size_t smem2 = (size_t)blk.x * blk.y * vec * sizeof(double) + 2 * (size_t)rch * ((size_t)g->k * 8 + 4);
-#define OSC_SPMM2_LAUNCH(R0)                                                                              \
+    const InitSrc none{nullptr, nullptr, nullptr, 0, 0};
+#define OSC_SPMM2_LAUNCH(R0, SRC)                                                                         \
   OSC_VEC_DISPATCH(vec, {                                                                                 \
     if (smem2 > 48 * 1024)                                                                                \
       OSC_CUDA(cudaFuncSetAttribute((const void*)pcg_spmm2_kernel<VEC, R0>,                               \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmmSmemMax));    \
     pcg_spmm2_kernel<VEC, R0><<<grid, blk, smem2, st>>>(to_dims(d), c, gview(g), cview(chain), gates,     \
-                                                       vv.all, vv.local_ids, out, Pout, part, rch, done); \
+                                                       vv.all, vv.local_ids, out, Pout, part, rch, done, \
+                                                       SRC);                                              \
   })
-    if (smem2 <= kSpmmSmemMax) {
-      if (res0) {
-        OSC_SPMM2_LAUNCH(true)
-      } else {
-        OSC_SPMM2_LAUNCH(false)
-      }
-      OSC_LAUNCH_CHECK("pcg_spmm2_kernel");
-      return OSC_OK;
+    if (init != nullptr) {
+      OSC_SPMM2_LAUNCH(2, *init)
+    } else if (res0) {
+      OSC_SPMM2_LAUNCH(1, none)
+    } else {
+      OSC_SPMM2_LAUNCH(0, none)
     }
 #undef OSC_SPMM2_LAUNCH
+    OSC_LAUNCH_CHECK("pcg_spmm2_kernel");
+    return OSC_OK;
   }
 #define OSC_SPMM_LAUNCH(R0)                                                                               \
   OSC_VEC_DISPATCH(vec, {                                                                                 \
@@ -913,7 +967,7 @@ int pcg_pupdate(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, floa
 
 int pcg_pupdate_x(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, float dt, int jacobi,
                   const float* gates, const float* rz_new, const float* rz_old, const float* pap, const float* R,
-                  float* P, float* X, const PcgCtl* ctl, int it, int x_only, cudaStream_t st) {
+                  float* P, float* X, const PcgCtl* ctl, int it, int x_only, cudaStream_t st, const float* Xsrc) {
   if (d->n_local == 0) return OSC_OK;
   int vec;
   dim3 blk;
@@ -921,7 +975,8 @@ int pcg_pupdate_x(const osc_pcg_dims_t* d, const osc_params_t* prm, int mode, fl
   Coef c = make_coef(prm, mode, dt, jacobi);
   const int64_t total = d->n_local * (d->D / vec);
   OSC_VEC_DISPATCH(vec, pcg_pupdate_x_kernel<VEC><<<ew_grid(total), 256, 0, st>>>(
-                            to_dims(d), c, gates, rz_new, rz_old, pap, R, P, X, ctl, it, x_only);)
+                            to_dims(d), c, gates, rz_new, rz_old, pap, R, P, X, ctl, it, x_only,
+                            Xsrc != nullptr ? Xsrc : X);)
   OSC_LAUNCH_CHECK("pcg_pupdate_x_kernel");
   return OSC_OK;
 }
@@ -1013,10 +1068,12 @@ CtlPoll* ctl_poll() {
 // The stop test runs on the device (pcg_decide) and the host enqueues ONE iteration ahead of it: the
 // kernels of an iteration that follows the stop return at once, so the result is the reference's and
 // the stream never drains between iterations.
+// `init` (optional): fused start -- X and R are NOT initialised by the caller; x0 = init->x0, the right-hand
+// side is formed inside the first residual, and X is first written by the x update of iteration 1.
 static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_chain_t* chain,
                     const osc_params_t* prm, int mode, float dt, int jacobi, double tol, int max_iters,
                     const float* gates, float* X, float* R, Arena& ar, int* h_iters, float* h_res,
-                    cudaStream_t st) {
+                    cudaStream_t st, const InitSrc* init = nullptr, const float* x0 = nullptr) {
   const int D = d.D;
   const size_t nd = (size_t)g->N * D;
   float* P = ar.take<float>(nd);
@@ -1036,7 +1093,13 @@ static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_cha
   const bool fuse_x = pcg_fuse_x();
   int rc;
   OSC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PcgCtl), st));
-  if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) return rc;
+  if (init != nullptr) {
+    if ((rc = spmm_launch(true, &d, g, chain, prm, mode, dt, jacobi, gates, VecView{x0, nullptr, 0, 0}, R, P, part_a,
+                          st, nullptr, init)))
+      return rc;
+  } else if ((rc = pcg_residual0(&d, g, chain, prm, mode, dt, jacobi, gates, X, R, P, part_a, st))) {
+    return rc;
+  }
   if ((rc = pcg_reduce(part_a, d.n_blocks, D, rz, nullptr, nullptr, st))) return rc;
   PcgCtl h{0, 0, __builtin_nanf(""), 0};
   int it = 0;
@@ -1051,7 +1114,8 @@ static int pcg_core(const osc_pcg_dims_t& d, const osc_graph_t* g, const osc_cha
     if ((rc = pcg_decide(ctl, nullptr, d_res, D, tol, it, max_iters, st))) return rc;
     if ((rc = poll->record(it, ctl, st))) return rc;
     // x += alpha p always belongs to this iteration; p = z + beta p only if it was not the last
-    if (fuse_x && (rc = pcg_pupdate_x(&d, prm, mode, dt, jacobi, gates, rz_new, rz, pap, R, P, X, ctl, it, 0, st)))
+    if (fuse_x && (rc = pcg_pupdate_x(&d, prm, mode, dt, jacobi, gates, rz_new, rz, pap, R, P, X, ctl, it, 0, st,
+                                      (init != nullptr && it == 1) ? x0 : nullptr)))
       return rc;
     if (it > 1) {  // the previous iteration's verdict has landed (or lands while this one runs)
       if ((rc = poll->wait(it - 1, &h))) return rc;
@@ -1089,6 +1153,16 @@ int pcg_solve(const osc_graph_t* g, const osc_chain_t* chain, const osc_params_t
   Arena ar(workspace, ws_bytes);
   float* R = ar.take<float>((size_t)g->N * D);
   if (!ar.ok) return fail(OSC_ERR_WORKSPACE, "pcg_solve: workspace too small");
+  // start vector of lattice.py:751-758: Y (stationary solve, cold start), U (warm, no inertia), else a mix
+  const bool settle = mode == OSC_MODE_SETTLE;
+  const bool mixed = settle && warm && inertia > 0.f;
+  const float* x0 = (!settle || !warm) ? Y : U;
+  if (max_iters >= 1 && !mixed && pcg_fuse_x() && pcg_fused_init_ok(&d, g) && x0 != X) {
+    // no setup pass: the first residual forms the right-hand side itself and gathers the start vector in place
+    const InitSrc init{Y, U, psi, x0 == Y ? 1 : 0, x0 == U ? 1 : 0};
+    return pcg_core(d, g, chain, prm, mode, dt, jacobi, tol, max_iters, gates, X, R, ar, h_iters, h_res, st, &init,
+                    x0);
+  }
   if ((rc = pcg_setup(&d, prm, mode, dt, warm, inertia, Y, U, psi, gates, X, R, st))) return rc;
   if (max_iters < 1) return OSC_OK;  // no iteration: X = x0 (never uninitialised memory)
   return pcg_core(d, g, chain, prm, mode, dt, jacobi, tol, max_iters, gates, X, R, ar, h_iters, h_res, st);

@@ -36,9 +36,19 @@ int pcg_max_ell_width(int D);
 int pcg_setup(const osc_pcg_dims_t*, const osc_params_t*, int mode, float dt, int warm, float inertia,
               const float* Y, const float* U, const float* psi, const float* gates, float* X, float* Bv,
               cudaStream_t);
+// Fused first residual: the right-hand side is formed inside the SpMM from Y, U and psi (rows of the local
+// block), and the gathered vector is the start vector itself -- Y (y_is_x0) or U (u_is_x0).
+struct InitSrc {
+  const float* Y;
+  const float* U;
+  const float* psi;
+  int y_is_x0, u_is_x0;
+};
+bool pcg_fused_init_ok(const osc_pcg_dims_t* d, const osc_graph_t* g);
 int spmm_launch(bool res0, const osc_pcg_dims_t* d, const osc_graph_t* g, const osc_chain_t* chain,
                 const osc_params_t* prm, int mode, float dt, int jacobi, const float* gates, VecView vv,
-                float* out, float* Pout, double* part, cudaStream_t st, const int* done = nullptr);
+                float* out, float* Pout, double* part, cudaStream_t st, const int* done = nullptr,
+                const InitSrc* init = nullptr);
 int pcg_residual0(const osc_pcg_dims_t*, const osc_graph_t*, const osc_chain_t*, const osc_params_t*,
                   int mode, float dt, int jacobi, const float* gates, const float* Xall, float* RBv,
                   float* P, double* part_rz, cudaStream_t);
@@ -64,7 +74,7 @@ bool pcg_fuse_x();
 // x += alpha p fused with p = z + beta p (after the iteration's verdict; see pcg_pupdate_x_kernel)
 int pcg_pupdate_x(const osc_pcg_dims_t*, const osc_params_t*, int mode, float dt, int jacobi, const float* gates,
                   const float* rz_new, const float* rz_old, const float* pap, const float* R, float* P, float* X,
-                  const PcgCtl* ctl, int it, int x_only, cudaStream_t st);
+                  const PcgCtl* ctl, int it, int x_only, cudaStream_t st, const float* Xsrc = nullptr);
 // stop test on the device: res = max_c sqrt(rr_c) from the column sums rr[D] (or, if rr == nullptr, the
 // already reduced *d_res); records {iters = it, res}; sets done when res <= tol or it >= max_iters
 int pcg_decide(PcgCtl* ctl, const float* rr, const float* d_res, int D, double tol, int it, int max_iters,

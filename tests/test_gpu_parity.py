@@ -641,3 +641,36 @@ def test_deferred_x_update_is_bit_identical(monkeypatch):
     assert a[3] == b[3] and a[4] == b[4]
     assert np.array_equal(a[5], b[5])
     assert np.array_equal(a[6], b[6])
+
+
+@pytest.mark.parametrize("warm", [False, True])
+def test_fused_first_residual_is_bit_identical(monkeypatch, warm):
+    """osc_pcg_solve / osc_dist_pcg_solve skip the setup pass when the start vector is Y or U itself: the first
+    residual forms the right-hand side in place (pcg_setup_kernel's arithmetic) and X is first written by the x
+    update of iteration 1.  Cold start, warm start from a previous settle, gates, a chain, and U*: no bit moves."""
+    import oscillink_b200 as api
+    from oscillink_b200.sharded_api import ShardedLattice
+
+    rs = np.random.RandomState(33)
+    Y = rs.randn(2500, 64).astype(np.float32)
+    psi = Y[:32].mean(axis=0)
+    psi = (psi / np.linalg.norm(psi)).astype(np.float32)
+    gates = rs.uniform(0.2, 1.0, size=2500).astype(np.float32)
+    out = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("OSC_PCG_FUSE_INIT", fuse)
+        lat = api.OscillinkLattice(Y, kneighbors=6, deterministic_k=True)
+        lat.set_query(psi, gates=gates)
+        lat.add_chain([5, 50, 500, 1500], lamP=0.2)
+        a = lat.settle(max_iters=3, tol=1e-9, warm_start=warm)
+        U1 = lat.U.copy()
+        b = lat.settle(max_iters=12, tol=1e-3, warm_start=warm)
+        import torch
+
+        sl = ShardedLattice(torch.as_tensor(Y).cuda(), 2500, kneighbors=6)
+        sl.set_query(psi)
+        c = sl.settle(max_iters=12, tol=1e-3)
+        out[fuse] = (a["iters"], a["res"], U1, b["iters"], b["res"], lat.U.copy(), lat.solve_Ustar().copy(),
+                     c["iters"], c["res"], sl.U_full())
+    for x, y in zip(out["0"], out["1"]):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
