@@ -297,6 +297,15 @@ batched_pack8_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ 
     }
     left[r] = cnt[r];
   }
+  // 4-bit count per residue (column & 7) over a row's UNUSED entries, kept up to date as entries are placed
+  unsigned rcw[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    rcw[r] = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (e < cnt[r]) rcw[r] += 1u << ((idx[r][e] & 7) * 4);
+  }
   ushort4 jbuf[8];
   float4 wbuf[8];
 #pragma unroll 1
@@ -311,10 +320,6 @@ batched_pack8_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ 
       for (int r = 0; r < 8; ++r) {
         const bool must = left[r] >= (KP - t);
         if (pick_e[r] < 0 && left[r] != 0 && ((ps == 0) == must)) {
-          unsigned rcw = 0;  // 4-bit count per residue over the unused entries
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (e < cnt[r] && !((used[r] >> e) & 1u)) rcw += 1u << ((idx[r][e] & 7) * 4);
           int best = -1, sel = -1, sel_j = 0, first = -1, first_j = 0;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -324,7 +329,7 @@ batched_pack8_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ 
                 first_j = idx[r][e];
               }
               const int res = idx[r][e] & 7;
-              const int c = (int)((rcw >> (res * 4)) & 15u);
+              const int c = (int)((rcw[r] >> (res * 4)) & 15u);
               if (!((taken >> res) & 1u) && c > best) {
                 best = c;
                 sel = e;
@@ -340,6 +345,7 @@ batched_pack8_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ 
             pick_e[r] = sel;
             pick_j[r] = sel_j;
             used[r] |= 1u << sel;
+            rcw[r] -= 1u << ((sel_j & 7) * 4);
             left[r]--;
             taken |= 1u << (sel_j & 7);
           }

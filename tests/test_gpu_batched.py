@@ -309,6 +309,28 @@ def test_register_resident_build_kernels_are_bit_identical(N, D, k, switch, monk
         assert np.array_equal(a, b)
 
 
+def test_register_resident_packer_gives_the_same_graph_image(monkeypatch):
+    """batched_pack8_kernel (k <= 8: bank-residue scheduling of the neighbour slots with the row entries and
+    the residue counts in registers) against the generic batched_pack_kernel: the slot order fixes the order of
+    the gather sums, so identical images <=> bit-identical settles."""
+    import torch
+
+    from oscillink_b200 import BatchedLattices
+
+    Y, psi = _inputs(4, 1200, 384, seed0=1300)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("OSC_BATCHED_PACK8", flag)
+        bl = BatchedLattices(Y, kneighbors=8)
+        bl.set_query(psi)
+        out = bl.settle(max_iters=12, tol=1e-3, receipt=True, keep_ustar=True)
+        torch.cuda.synchronize()
+        res.append((bl.U.cpu().numpy(), bl.Ustar.cpu().numpy(), out["deltaH"].cpu().numpy(),
+                    out["iters"].cpu().numpy(), out["res"].cpu().numpy()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+
+
 def test_settle_host_batch_returns_the_settled_state():
     """settle_host_batch(U_host=...): the settled U of every lattice comes back through a third stream."""
     import torch
